@@ -1,0 +1,845 @@
+// g6_context.cu -- host side of the B200 g6 library: device state, staging,
+// kernel selection and the C ABI declared in include/g6_b200.h.
+//
+// Mirrors the behaviour (not the code) of the reference host shells
+//   lib/sapporo_light/sapporo.cpp:19-272, send_fetch_data.cpp:30-167,
+//   host_evaluate_gravity.cu:31-159, sapporoG6lib.cpp:3-81
+// with the limits lifted (dynamic j capacity instead of 131072; 16384 pipes
+// instead of 256) and no per-call blocking cudaMemcpy chain: one pinned
+// staging buffer per direction, one stream, everything asynchronous until
+// g6calc_lasthalf*_ has to hand results to the caller.
+//
+// There is NO CPU fallback: without a CUDA device g6_open_ fails loudly.
+
+#include "g6_kernels.cuh"
+#include "../../include/g6_b200.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+using namespace g6b;
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            fprintf(stderr, "g6_b200: FATAL CUDA error %s at %s:%d: %s\n", cudaGetErrorName(e_),   \
+                    __FILE__, __LINE__, cudaGetErrorString(e_));                                   \
+            exit(-1);                                                                              \
+        }                                                                                          \
+    } while (0)
+
+namespace {
+
+// Force-kernel variants (g6x_set_variant ids).
+enum Variant {
+    V_AUTO = 0,
+    V_S4 = 1,    // scalar, 4 i/thread, 256 i-slots  (IB 1024)
+    V_S2 = 2,    // scalar, 2 i/thread, 256 i-slots  (IB 512)
+    V_S1 = 3,    // scalar, 1 i/thread, 256 i-slots  (IB 256)
+    V_W1 = 4,    // scalar, 1 i/thread, 32 i-slots x 8 j-slots (IB 32)
+    V_T1 = 5,    // scalar, 1 i/thread, 4 i-slots x 64 j-slots (IB 4)
+    V_P4 = 6,    // packed f32x2, 4 i/thread, 256 i-slots (IB 1024)
+    V_P2 = 7,    // packed f32x2, 2 i/thread, 256 i-slots (IB 512)
+    V_P2W = 8,   // packed f32x2, 2 i/thread, 32 i-slots x 8 j-slots (IB 64)
+    V_COUNT
+};
+
+struct VariantInfo {
+    int ib;          // i-particles per CTA
+    int ctas_per_sm; // resident CTAs targeted
+};
+
+struct Context {
+    bool open = false;
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    int npipes = 16384;
+    int ngb_cap = 1024;
+    int variant = V_AUTO;
+    int j_offset = 0;
+    long long launches = 0;
+
+    // j state
+    int capacity = 0;  // slots allocated (multiple of TILE)
+    int nj_hi = 0;     // 1 + highest address ever set
+    JState js{};
+    double ti = 0.0;
+    double predicted_ti = 0.0;
+    int predicted_nj = -1;  // prefix predicted at predicted_ti (-1: none)
+    bool j_dirty = false;
+
+    // staging of j-updates
+    std::vector<int> slot_of_addr;  // address -> slot in the pending batch, -1
+    JUpdate *h_up = nullptr;        // pinned
+    JUpdate *d_up = nullptr;
+    int up_cap = 0, up_n = 0;
+
+    // i-block buffers (npipes)
+    float4 *h_i = nullptr;  // pinned [3][npipes]
+    float4 *d_i = nullptr;  // [3][npipes]
+    double *d_sum = nullptr;
+    u64 *d_key = nullptr;
+    int *d_nnid = nullptr;
+    double *h_sum = nullptr;  // pinned
+    int *h_nnid = nullptr;    // pinned
+    // device-resident entry point scratch
+    float4 *d_i2 = nullptr;
+    // partial workspace
+    double *part_sum = nullptr;
+    u64 *part_key = nullptr;
+    size_t part_records = 0;
+    unsigned int *tickets = nullptr;
+    // neighbour lists
+    int *d_ngb_cnt = nullptr, *d_ngb_list = nullptr;
+    int *h_ngb_cnt = nullptr, *h_ngb_list = nullptr;
+    bool ngb_valid = false;    // lists of the last lasthalf2 are on the device
+    bool ngb_fetched = false;  // ... and on the host
+
+    // captured by firsthalf
+    int cur_ni = 0, cur_nj = 0;
+    float cur_eps2 = 0.f;
+    bool cur_any_h2 = false;
+    bool pending = false;
+};
+
+Context G;
+
+int env_int(const char *name, int dflt)
+{
+    const char *s = getenv(name);
+    if (!s || !*s) return dflt;
+    return atoi(s);
+}
+
+template <typename T>
+void dev_alloc(T *&p, size_t n)
+{
+    CK(cudaMalloc((void **)&p, std::max<size_t>(n, 1) * sizeof(T)));
+}
+template <typename T>
+void dev_free(T *&p)
+{
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+template <typename T>
+void host_alloc(T *&p, size_t n)
+{
+    CK(cudaMallocHost((void **)&p, std::max<size_t>(n, 1) * sizeof(T)));
+}
+template <typename T>
+void host_free(T *&p)
+{
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+}
+
+template <typename T>
+void grow_dev(T *&p, size_t old_n, size_t new_n, cudaStream_t st)
+{
+    T *q = nullptr;
+    dev_alloc(q, new_n);
+    CK(cudaMemsetAsync(q, 0, new_n * sizeof(T), st));
+    if (p && old_n) CK(cudaMemcpyAsync(q, p, old_n * sizeof(T), cudaMemcpyDeviceToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    if (p) cudaFree(p);
+    p = q;
+}
+
+void ensure_capacity(int need)
+{
+    if (need <= G.capacity) return;
+    size_t newcap = std::max<size_t>(G.capacity ? (size_t)G.capacity * 2 : 65536, (size_t)need);
+    newcap = (newcap + TILE - 1) / TILE * TILE;
+    size_t old = G.capacity;
+    grow_dev(G.js.xy, old, newcap, G.stream);
+    grow_dev(G.js.zt, old, newcap, G.stream);
+    grow_dev(G.js.vxy, old, newcap, G.stream);
+    grow_dev(G.js.vz, old, newcap, G.stream);
+    grow_dev(G.js.am, old, newcap, G.stream);
+    grow_dev(G.js.jk, old, newcap, G.stream);
+    grow_dev(G.js.A, old, newcap, G.stream);
+    grow_dev(G.js.B, old, newcap, G.stream);
+    grow_dev(G.js.C, old, newcap, G.stream);
+    G.capacity = (int)newcap;
+    G.slot_of_addr.resize(newcap, -1);
+    G.predicted_nj = -1;
+}
+
+void ensure_up_cap(int need)
+{
+    if (need <= G.up_cap) return;
+    int newcap = std::max(need, std::max(4096, G.up_cap * 2));
+    JUpdate *nh = nullptr;
+    host_alloc(nh, newcap);
+    if (G.h_up && G.up_n) memcpy(nh, G.h_up, sizeof(JUpdate) * G.up_n);
+    host_free(G.h_up);
+    G.h_up = nh;
+    CK(cudaStreamSynchronize(G.stream));
+    dev_free(G.d_up);
+    dev_alloc(G.d_up, newcap);
+    G.up_cap = newcap;
+}
+
+void require_open(const char *fn)
+{
+    if (!G.open) {
+        fprintf(stderr, "g6_b200: FATAL %s called before g6_open_\n", fn);
+        exit(-1);
+    }
+}
+
+// Upload the pending j-updates and scatter them into the state arrays.
+void flush_updates()
+{
+    if (G.up_n == 0) return;
+    CK(cudaMemcpyAsync(G.d_up, G.h_up, sizeof(JUpdate) * G.up_n, cudaMemcpyHostToDevice, G.stream));
+    scatter_kernel<<<(G.up_n + 255) / 256, 256, 0, G.stream>>>(G.up_n, G.d_up, G.js);
+    G.launches++;
+    CK(cudaGetLastError());
+    // the pinned batch is reused by the next set_j_particle: wait for the copy
+    CK(cudaStreamSynchronize(G.stream));
+    for (int k = 0; k < G.up_n; k++) G.slot_of_addr[G.h_up[k].addr] = -1;
+    G.up_n = 0;
+    G.j_dirty = true;
+}
+
+void run_predictor(int nj)
+{
+    if (nj > G.capacity) nj = G.capacity;
+    if (nj <= 0) return;
+    if (!G.j_dirty && G.predicted_nj >= nj && G.predicted_ti == G.ti) return;
+    int n = std::max(nj, std::min(G.nj_hi, G.capacity));
+    predict_kernel<<<(n + 255) / 256, 256, 0, G.stream>>>(n, G.ti, G.js);
+    G.launches++;
+    CK(cudaGetLastError());
+    G.predicted_nj = n;
+    G.predicted_ti = G.ti;
+    G.j_dirty = false;
+}
+
+void ensure_partials(size_t records)
+{
+    if (records <= G.part_records) return;
+    CK(cudaStreamSynchronize(G.stream));
+    dev_free(G.part_sum);
+    dev_free(G.part_key);
+    dev_alloc(G.part_sum, records * 7);
+    dev_alloc(G.part_key, records);
+    G.part_records = records;
+}
+
+template <int IPT, int NI_SLOTS, bool PACKED, int MINB>
+void launch_variant(const ForceArgs &a, dim3 grid, bool nn, bool list, cudaStream_t st)
+{
+    size_t smem = sizeof(ForceSmem);
+#define G6_LAUNCH(NN_, LIST_)                                                                       \
+    do {                                                                                            \
+        auto kern = force_kernel<IPT, NI_SLOTS, NN_, LIST_, PACKED, MINB>;                          \
+        static bool attr_set = false;                                                               \
+        if (!attr_set) {                                                                            \
+            CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            attr_set = true;                                                                        \
+        }                                                                                           \
+        kern<<<grid, THREADS, smem, st>>>(a);                                                       \
+    } while (0)
+    if (list)
+        G6_LAUNCH(true, true);
+    else if (nn)
+        G6_LAUNCH(true, false);
+    else
+        G6_LAUNCH(false, false);
+#undef G6_LAUNCH
+    CK(cudaGetLastError());
+}
+
+const VariantInfo &variant_info(int v)
+{
+    static const VariantInfo info[V_COUNT] = {
+        {0, 0}, {1024, 1}, {512, 2}, {256, 2}, {32, 2}, {4, 2}, {1024, 1}, {512, 2}, {64, 2},
+    };
+    return info[v];
+}
+
+int choose_variant(int ni)
+{
+    if (G.variant != V_AUTO) return G.variant;
+    if (ni > 1536) return V_P4;
+    if (ni > 384) return V_P2;
+    if (ni > 48) return V_P2W;
+    if (ni > 4) return V_W1;
+    return V_T1;
+}
+
+// Launch the force kernel for i-block (iA,iB,iC) of ni particles against j in [0,nj).
+void launch_force(int nj, int ni, const float4 *iA, const float4 *iB, const float4 *iC, float eps2, bool nn,
+                  bool list, double *out_sum, u64 *out_key, int *out_nnid)
+{
+    if (nj > G.capacity) nj = G.capacity;
+    int v = choose_variant(ni);
+    const VariantInfo &vi = variant_info(v);
+    int n_iblocks = (ni + vi.ib - 1) / vi.ib;
+    int ntiles = (nj + TILE - 1) / TILE;
+    if (ntiles < 1) ntiles = 1;
+    // j-splits: fill the machine (resident CTAs x ~2 waves when there is work), >= 2 tiles per split
+    int target = G.sm_count * vi.ctas_per_sm;
+    int nsplit = (target + n_iblocks - 1) / n_iblocks;
+    if ((long long)n_iblocks * nsplit < 2LL * target && ntiles / std::max(nsplit, 1) >= 16) nsplit *= 2;
+    nsplit = std::min(nsplit, std::max(1, ntiles / 2));
+    nsplit = std::max(nsplit, 1);
+    int tps = (ntiles + nsplit - 1) / nsplit;
+    nsplit = (ntiles + tps - 1) / tps;
+
+    ForceArgs a{};
+    a.jA = G.js.A; a.jB = G.js.B; a.jC = G.js.C;
+    a.iA = iA; a.iB = iB; a.iC = iC;
+    a.ni = ni; a.nj = nj;
+    a.tiles_per_split = tps; a.nsplit = nsplit;
+    a.ni_pad = ni;
+    a.j_offset = G.j_offset;
+    a.eps2 = eps2;
+    if (nsplit > 1) ensure_partials((size_t)nsplit * ni);
+    a.part_sum = G.part_sum; a.part_key = G.part_key;
+    a.tickets = G.tickets;
+    a.out_sum = out_sum; a.out_key = out_key; a.out_nnid = out_nnid;
+    a.ngb_cnt = G.d_ngb_cnt; a.ngb_list = G.d_ngb_list; a.ngb_cap = G.ngb_cap;
+    dim3 grid(nsplit, n_iblocks);
+    switch (v) {
+        case V_S4: launch_variant<4, 256, false, 1>(a, grid, nn, list, G.stream); break;
+        case V_S2: launch_variant<2, 256, false, 2>(a, grid, nn, list, G.stream); break;
+        case V_S1: launch_variant<1, 256, false, 2>(a, grid, nn, list, G.stream); break;
+        case V_W1: launch_variant<1, 32, false, 2>(a, grid, nn, list, G.stream); break;
+        case V_T1: launch_variant<1, 4, false, 2>(a, grid, nn, list, G.stream); break;
+        case V_P4: launch_variant<4, 256, true, 1>(a, grid, nn, list, G.stream); break;
+        case V_P2: launch_variant<2, 256, true, 2>(a, grid, nn, list, G.stream); break;
+        case V_P2W: launch_variant<2, 32, true, 2>(a, grid, nn, list, G.stream); break;
+        default:
+            fprintf(stderr, "g6_b200: FATAL unknown force variant %d\n", v);
+            exit(-1);
+    }
+    G.launches++;
+}
+
+void free_all()
+{
+    dev_free(G.js.xy); dev_free(G.js.zt); dev_free(G.js.vxy); dev_free(G.js.vz);
+    dev_free(G.js.am); dev_free(G.js.jk); dev_free(G.js.A); dev_free(G.js.B); dev_free(G.js.C);
+    dev_free(G.d_up); host_free(G.h_up);
+    host_free(G.h_i); dev_free(G.d_i); dev_free(G.d_i2);
+    dev_free(G.d_sum); dev_free(G.d_key); dev_free(G.d_nnid);
+    host_free(G.h_sum); host_free(G.h_nnid);
+    dev_free(G.part_sum); dev_free(G.part_key); dev_free(G.tickets);
+    dev_free(G.d_ngb_cnt); dev_free(G.d_ngb_list);
+    host_free(G.h_ngb_cnt); host_free(G.h_ngb_list);
+    G.capacity = 0; G.nj_hi = 0; G.up_cap = 0; G.up_n = 0; G.part_records = 0;
+    G.slot_of_addr.clear();
+    G.predicted_nj = -1; G.j_dirty = false; G.pending = false;
+    G.ngb_valid = G.ngb_fetched = false;
+}
+
+void stage_j(int address, int index, double tj, double mass, const double *j6, const double *a2, const double *v,
+             const double *x)
+{
+    if (address < 0) {
+        fprintf(stderr, "g6_b200: FATAL g6_set_j_particle address %d < 0\n", address);
+        exit(-1);
+    }
+    ensure_capacity(address + 1);
+    int slot = G.slot_of_addr[address];
+    if (slot < 0) {  // last write wins within a batch (sapporo.cpp:83-110)
+        ensure_up_cap(G.up_n + 1);
+        slot = G.up_n++;
+        G.slot_of_addr[address] = slot;
+    }
+    JUpdate &u = G.h_up[slot];
+    for (int k = 0; k < 3; k++) {
+        u.x[k] = x[k];
+        u.v[k] = v[k];
+        u.a[k] = (float)(2.0 * a2[k]);   // a2 = acc/2   (sapporo.cpp:94)
+        u.j[k] = (float)(6.0 * j6[k]);   // j6 = jerk/6  (sapporo.cpp:95)
+    }
+    u.t = tj;
+    u.m = (float)mass;
+    u.id = index;
+    u.addr = address;
+    u.pad = 0;
+    if (address + 1 > G.nj_hi) G.nj_hi = address + 1;
+}
+
+}  // namespace
+
+// ===========================================================================
+// Part 1: the GRAPE-6 ABI
+// ===========================================================================
+extern "C" {
+
+int get_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int g6_open_(int *id)
+{
+    int ndev = get_device_count();
+    if (ndev <= 0) {
+        fprintf(stderr, "g6_b200: FATAL no CUDA device found (this library has no CPU fallback)\n");
+        exit(-1);
+    }
+    int dev = id ? *id : 0;
+    if (env_int("G6_B200_DEVICE_MODULO", 0)) dev = ((dev % ndev) + ndev) % ndev;
+    if (dev < 0 || dev >= ndev) {
+        fprintf(stderr, "g6_b200: g6_open: no CUDA device with id %d (%d present)\n", dev, ndev);
+        return -1;
+    }
+    if (G.open) {
+        if (dev == G.device) return 0;
+        int d = G.device;
+        g6_close_(&d);
+    }
+    G.device = dev;
+    CK(cudaSetDevice(dev));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major < 10) {
+        fprintf(stderr, "g6_b200: FATAL device %d is sm_%d%d; this library is built for sm_100a only\n", dev,
+                prop.major, prop.minor);
+        exit(-1);
+    }
+    G.sm_count = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&G.own_stream, cudaStreamNonBlocking));
+    G.stream = G.own_stream;
+    G.npipes = std::max(1, env_int("G6_B200_NPIPES", 16384));
+    G.ngb_cap = std::max(1, env_int("G6_B200_NGB_CAP", 1024));
+    G.variant = env_int("G6_B200_VARIANT", V_AUTO);
+    host_alloc(G.h_i, (size_t)3 * G.npipes);
+    dev_alloc(G.d_i, (size_t)3 * G.npipes);
+    dev_alloc(G.d_i2, (size_t)3 * G.npipes);
+    dev_alloc(G.d_sum, (size_t)7 * G.npipes);
+    dev_alloc(G.d_key, (size_t)G.npipes);
+    dev_alloc(G.d_nnid, (size_t)G.npipes);
+    host_alloc(G.h_sum, (size_t)7 * G.npipes);
+    host_alloc(G.h_nnid, (size_t)G.npipes);
+    dev_alloc(G.tickets, 65536);
+    CK(cudaMemsetAsync(G.tickets, 0, 65536 * sizeof(unsigned int), G.stream));
+    G.ti = 0.0;
+    G.predicted_nj = -1;
+    G.j_offset = 0;
+    G.open = true;
+    if (env_int("G6_B200_VERBOSE", 0))
+        fprintf(stderr, "g6_b200: open device %d (%s, %d SMs), npipes %d\n", dev, prop.name, G.sm_count, G.npipes);
+    return 0;
+}
+
+int g6_close_(int *id)
+{
+    (void)id;
+    if (!G.open) return 0;
+    CK(cudaSetDevice(G.device));
+    CK(cudaStreamSynchronize(G.stream));
+    free_all();
+    if (G.own_stream) cudaStreamDestroy(G.own_stream);
+    G.own_stream = G.stream = nullptr;
+    G.open = false;
+    return 0;
+}
+
+int g6_npipes_(void)
+{
+    if (G.open) return G.npipes;
+    return std::max(1, env_int("G6_B200_NPIPES", 16384));
+}
+
+int g6_set_tunit_(void *unused) { (void)unused; return 0; }
+int g6_set_xunit_(void *unused) { (void)unused; return 0; }
+
+int g6_set_ti_(int *id, double *ti)
+{
+    (void)id;
+    require_open("g6_set_ti_");
+    G.ti = *ti;
+    return 0;
+}
+
+int g6_set_j_particle_(int *cluster_id, int *address, int *index, double *tj, double *dtj, double *mass,
+                       double k18[3], double j6[3], double a2[3], double v[3], double x[3])
+{
+    (void)cluster_id; (void)dtj; (void)k18;
+    require_open("g6_set_j_particle_");
+    stage_j(*address, *index, *tj, *mass, j6, a2, v, x);
+    return 0;
+}
+
+void g6calc_firsthalf_(int *cluster_id, int *nj, int *ni, int index[], double xi[][3], double vi[][3],
+                       double aold[][3], double j6old[][3], double phiold[], double *eps2, double h2[])
+{
+    (void)cluster_id; (void)aold; (void)j6old; (void)phiold;
+    require_open("g6calc_firsthalf_");
+    int n = *ni;
+    if (n > G.npipes || n < 0) {
+        fprintf(stderr, "g6_b200: FATAL g6calc_firsthalf ni = %d exceeds g6_npipes() = %d\n", n, G.npipes);
+        exit(-1);
+    }
+    if (G.pending) CK(cudaStreamSynchronize(G.stream));  // a firsthalf without its lasthalf
+    flush_updates();
+    run_predictor(*nj);
+    // pack the i-block: double -> double-single (sapporo.cpp:125-134)
+    float4 *A = G.h_i, *B = G.h_i + G.npipes, *C = G.h_i + 2 * (size_t)G.npipes;
+    bool any_h2 = false;
+    for (int i = 0; i < n; i++) {
+        double x = xi[i][0], y = xi[i][1], z = xi[i][2];
+        float xh = (float)x, yh = (float)y, zh = (float)z;
+        float hh = h2 ? (float)h2[i] : 0.f;
+        any_h2 |= (hh > 0.f);
+        A[i] = make_float4(xh, yh, zh, hh);
+        union { int i; float f; } cv;
+        cv.i = index[i];
+        B[i] = make_float4((float)(x - (double)xh), (float)(y - (double)yh), (float)(z - (double)zh), cv.f);
+        C[i] = make_float4((float)vi[i][0], (float)vi[i][1], (float)vi[i][2], 0.f);
+    }
+    if (n > 0) {
+        CK(cudaMemcpyAsync(G.d_i, A, sizeof(float4) * n, cudaMemcpyHostToDevice, G.stream));
+        CK(cudaMemcpyAsync(G.d_i + G.npipes, B, sizeof(float4) * n, cudaMemcpyHostToDevice, G.stream));
+        CK(cudaMemcpyAsync(G.d_i + 2 * (size_t)G.npipes, C, sizeof(float4) * n, cudaMemcpyHostToDevice, G.stream));
+    }
+    G.cur_ni = n;
+    G.cur_nj = *nj;
+    G.cur_eps2 = (float)*eps2;
+    G.cur_any_h2 = any_h2;
+    G.pending = true;
+    G.ngb_valid = G.ngb_fetched = false;
+}
+
+static int lasthalf_common(int nj, int ni, double acc[][3], double jerk[][3], double pot[], int *inn)
+{
+    require_open("g6calc_lasthalf_");
+    if (!G.pending || ni != G.cur_ni) {
+        fprintf(stderr, "g6_b200: FATAL g6calc_lasthalf without matching g6calc_firsthalf (ni %d vs %d)\n", ni,
+                G.cur_ni);
+        exit(-1);
+    }
+    (void)nj;
+    bool nn = (inn != nullptr);
+    bool list = nn && G.cur_any_h2;
+    if (ni > 0) {
+        if (list) {
+            if (!G.d_ngb_cnt) {
+                dev_alloc(G.d_ngb_cnt, (size_t)G.npipes);
+                dev_alloc(G.d_ngb_list, (size_t)G.npipes * G.ngb_cap);
+                host_alloc(G.h_ngb_cnt, (size_t)G.npipes);
+                host_alloc(G.h_ngb_list, (size_t)G.npipes * G.ngb_cap);
+            }
+            CK(cudaMemsetAsync(G.d_ngb_cnt, 0, sizeof(int) * ni, G.stream));
+        }
+        launch_force(G.cur_nj, ni, G.d_i, G.d_i + G.npipes, G.d_i + 2 * (size_t)G.npipes, G.cur_eps2, nn, list,
+                     G.d_sum, G.d_key, G.d_nnid);
+        CK(cudaMemcpyAsync(G.h_sum, G.d_sum, sizeof(double) * 7 * ni, cudaMemcpyDeviceToHost, G.stream));
+        if (nn) CK(cudaMemcpyAsync(G.h_nnid, G.d_nnid, sizeof(int) * ni, cudaMemcpyDeviceToHost, G.stream));
+        CK(cudaStreamSynchronize(G.stream));
+        for (int i = 0; i < ni; i++) {
+            const double *s = G.h_sum + (size_t)7 * i;
+            acc[i][0] = s[0]; acc[i][1] = s[1]; acc[i][2] = s[2];
+            jerk[i][0] = s[3]; jerk[i][1] = s[4]; jerk[i][2] = s[5];
+            pot[i] = -s[6];
+            if (nn) inn[i] = G.h_nnid[i];
+        }
+    }
+    G.pending = false;
+    G.ngb_valid = list;
+    G.ngb_fetched = false;
+    return 0;
+}
+
+int g6calc_lasthalf_(int *cluster_id, int *nj, int *ni, int index[], double xi[][3], double vi[][3], double *eps2,
+                     double h2[], double acc[][3], double jerk[][3], double pot[])
+{
+    (void)cluster_id; (void)index; (void)xi; (void)vi; (void)eps2; (void)h2;
+    return lasthalf_common(*nj, *ni, acc, jerk, pot, nullptr);
+}
+
+int g6calc_lasthalf2_(int *cluster_id, int *nj, int *ni, int index[], double xi[][3], double vi[][3], double *eps2,
+                      double h2[], double acc[][3], double jerk[][3], double pot[], int inn[])
+{
+    (void)cluster_id; (void)index; (void)xi; (void)vi; (void)eps2; (void)h2;
+    return lasthalf_common(*nj, *ni, acc, jerk, pot, inn);
+}
+
+int g6_initialize_jp_buffer_(int *cluster_id, int *buf_size) { (void)cluster_id; (void)buf_size; return 0; }
+int g6_flush_jp_buffer_(int *cluster_id) { (void)cluster_id; return 0; }
+int g6_reset_(int *cluster_id) { (void)cluster_id; return 0; }
+int g6_reset_fofpga_(int *cluster_id) { (void)cluster_id; return 0; }
+
+int g6_read_neighbour_list_(int *cluster_id)
+{
+    (void)cluster_id;
+    require_open("g6_read_neighbour_list_");
+    if (!G.ngb_valid) {
+        G.ngb_fetched = false;
+        return 0;  // no lists were requested (all h2 <= 0 or lasthalf without nn)
+    }
+    int ni = G.cur_ni;
+    CK(cudaMemcpyAsync(G.h_ngb_cnt, G.d_ngb_cnt, sizeof(int) * ni, cudaMemcpyDeviceToHost, G.stream));
+    CK(cudaMemcpyAsync(G.h_ngb_list, G.d_ngb_list, sizeof(int) * (size_t)ni * G.ngb_cap, cudaMemcpyDeviceToHost,
+                       G.stream));
+    CK(cudaStreamSynchronize(G.stream));
+    G.ngb_fetched = true;
+    int overflow = 0;
+    for (int i = 0; i < ni; i++)
+        if (G.h_ngb_cnt[i] > G.ngb_cap) overflow = 1;
+    return overflow;
+}
+
+int g6_get_neighbour_list_(int *cluster_id, int *ipipe, int *maxlength, int *n_neighbours, int neighbour_list[])
+{
+    (void)cluster_id;
+    require_open("g6_get_neighbour_list_");
+    int ip = *ipipe;
+    if (ip < 0 || ip >= G.cur_ni) {
+        fprintf(stderr, "g6_b200: FATAL g6_get_neighbour_list ipipe = %d >= ni = %d\n", ip, G.cur_ni);
+        exit(-1);  // as sapporo.cpp:254-258
+    }
+    if (!G.ngb_valid || !G.ngb_fetched) {
+        *n_neighbours = 0;
+        return 0;
+    }
+    int cnt = G.h_ngb_cnt[ip];
+    int have = std::min(cnt, G.ngb_cap);
+    int *src = G.h_ngb_list + (size_t)ip * G.ngb_cap;
+    std::sort(src, src + have);
+    int ncopy = std::min(have, *maxlength);
+    memcpy(neighbour_list, src, sizeof(int) * ncopy);
+    *n_neighbours = cnt;
+    return (cnt > *maxlength || cnt > G.ngb_cap) ? 1 : 0;
+}
+
+// ---- by-value variants (lib/g6lib/g6lib.h:58-128) ---------------------------
+int g6_open(int clusterid) { return g6_open_(&clusterid); }
+int g6_close(int clusterid) { return g6_close_(&clusterid); }
+int g6_npipes(void) { return g6_npipes_(); }
+int g6_set_tunit(int newtunit) { (void)newtunit; return 0; }
+int g6_set_xunit(int newxunit) { (void)newxunit; return 0; }
+int g6_set_ti(int clusterid, double ti) { return g6_set_ti_(&clusterid, &ti); }
+int g6_set_j_particle(int clusterid, int address, int index, double tj, double dtj, double mass, double a2by18[3],
+                      double a1by6[3], double aby2[3], double v[3], double x[3])
+{
+    return g6_set_j_particle_(&clusterid, &address, &index, &tj, &dtj, &mass, a2by18, a1by6, aby2, v, x);
+}
+void g6calc_firsthalf(int clusterid, int nj, int ni, int index[], double xi[][3], double vi[][3], double fold[][3],
+                      double jold[][3], double phiold[], double eps2, double h2[])
+{
+    g6calc_firsthalf_(&clusterid, &nj, &ni, index, xi, vi, fold, jold, phiold, &eps2, h2);
+}
+int g6calc_lasthalf(int clusterid, int nj, int ni, int index[], double xi[][3], double vi[][3], double eps2,
+                    double h2[], double acc[][3], double jerk[][3], double pot[])
+{
+    return g6calc_lasthalf_(&clusterid, &nj, &ni, index, xi, vi, &eps2, h2, acc, jerk, pot);
+}
+int g6calc_lasthalf2(int clusterid, int nj, int ni, int index[], double xi[][3], double vi[][3], double eps2,
+                     double h2[], double acc[][3], double jerk[][3], double pot[], int nnbindex[])
+{
+    return g6calc_lasthalf2_(&clusterid, &nj, &ni, index, xi, vi, &eps2, h2, acc, jerk, pot, nnbindex);
+}
+int g6_initialize_jp_buffer(int clusterid, int size) { (void)clusterid; (void)size; return 0; }
+int g6_flush_jp_buffer(int clusterid) { (void)clusterid; return 0; }
+void g6_reset(int devid) { (void)devid; }
+int g6_reset_fofpga(int devid) { (void)devid; return 0; }
+void g6_reinitialize(int clusterid) { (void)clusterid; }
+int g6_get_number_of_pipelines(void) { return g6_npipes_(); }
+int g6_read_neighbour_list(int clusterid) { return g6_read_neighbour_list_(&clusterid); }
+int g6_get_neighbour_list(int clusterid, int ipipe, int maxlength, int *nblen, int nbl[])
+{
+    return g6_get_neighbour_list_(&clusterid, &ipipe, &maxlength, nblen, nbl);
+}
+static int g_sort_mode = 1;
+void g6_set_neighbour_list_sort_mode(int mode) { g_sort_mode = mode; }
+int g6_get_neighbour_list_sort_mode(void) { return g_sort_mode; }
+int g6_set_overflow_flag_test_mode(int aflag, int jflag, int pflag) { (void)aflag; (void)jflag; (void)pflag; return 0; }
+void force_j_particle_send(void)
+{
+    if (G.open) flush_updates();
+}
+
+// ===========================================================================
+// Part 2: g6x_ extensions
+// ===========================================================================
+int g6x_version(void) { return 100; }
+
+int g6x_set_stream(void *cuda_stream)
+{
+    require_open("g6x_set_stream");
+    CK(cudaStreamSynchronize(G.stream));
+    G.stream = cuda_stream ? (cudaStream_t)cuda_stream : G.own_stream;
+    return 0;
+}
+
+int g6x_set_j_offset(int offset)
+{
+    G.j_offset = offset;
+    return 0;
+}
+
+int g6x_set_j_particles(int n, const int *address, int address0, const int *index, const double *tj,
+                        const double *mass, const double (*j6)[3], const double (*a2)[3], const double (*v)[3],
+                        const double (*x)[3])
+{
+    require_open("g6x_set_j_particles");
+    static const double zero3[3] = {0, 0, 0};
+    if (n <= 0) return 0;
+    int maxaddr = address0 + n - 1;
+    if (address)
+        for (int k = 0; k < n; k++) maxaddr = std::max(maxaddr, address[k]);
+    ensure_capacity(maxaddr + 1);
+    ensure_up_cap(G.up_n + n);
+    for (int k = 0; k < n; k++)
+        stage_j(address ? address[k] : address0 + k, index[k], tj ? tj[k] : 0.0, mass[k], j6 ? j6[k] : zero3,
+                a2 ? a2[k] : zero3, v[k], x[k]);
+    return 0;
+}
+
+int g6x_predict(int nj, double ti)
+{
+    require_open("g6x_predict");
+    G.ti = ti;
+    flush_updates();
+    run_predictor(nj);
+    return 0;
+}
+
+int g6x_calc_device(int nj, int ni, const int *d_index, const double *d_xi, const double *d_vi, const double *d_h2,
+                    double eps2, int flags, double *d_sum, unsigned long long *d_key, int *d_nnid)
+{
+    require_open("g6x_calc_device");
+    flush_updates();
+    run_predictor(nj);
+    bool nn = (flags & 1) != 0, list = (flags & 2) != 0;
+    if (list) {
+        fprintf(stderr, "g6_b200: FATAL g6x_calc_device: neighbour lists are served by the g6 ABI path only\n");
+        exit(-1);
+    }
+    for (int i0 = 0; i0 < ni; i0 += G.npipes) {
+        int n = std::min(G.npipes, ni - i0);
+        float4 *A = G.d_i2, *B = G.d_i2 + G.npipes, *C = G.d_i2 + 2 * (size_t)G.npipes;
+        pack_i_kernel<<<(n + 255) / 256, 256, 0, G.stream>>>(n, d_index + i0, d_xi + 3 * (size_t)i0,
+                                                              d_vi + 3 * (size_t)i0, d_h2 ? d_h2 + i0 : nullptr, A, B,
+                                                              C);
+        G.launches++;
+        CK(cudaGetLastError());
+        launch_force(nj, n, A, B, C, (float)eps2, nn, false, d_sum + 7 * (size_t)i0, d_key + i0, d_nnid + i0);
+    }
+    return 0;
+}
+
+int g6x_resolve_nn(int ni, const unsigned long long *d_key, int rank, int *d_nnid)
+{
+    require_open("g6x_resolve_nn");
+    if (ni <= 0) return 0;
+    resolve_nn_kernel<<<(ni + 255) / 256, 256, 0, G.stream>>>(ni, d_key, rank, G.j_offset,
+                                                               std::min(G.nj_hi, G.capacity), G.js.B, d_nnid);
+    G.launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int g6x_synchronize(void)
+{
+    require_open("g6x_synchronize");
+    CK(cudaStreamSynchronize(G.stream));
+    return 0;
+}
+
+long long g6x_launch_count(void) { return G.launches; }
+
+int g6x_get_predicted(void **A, void **B, void **C, int *capacity)
+{
+    require_open("g6x_get_predicted");
+    *A = G.js.A; *B = G.js.B; *C = G.js.C;
+    *capacity = G.capacity;
+    return 0;
+}
+
+int g6x_read_predicted(int nj, double (*pos)[3], double (*vel)[3])
+{
+    require_open("g6x_read_predicted");
+    nj = std::min(nj, G.capacity);
+    std::vector<float4> A(nj), B(nj), C(nj);
+    CK(cudaStreamSynchronize(G.stream));
+    CK(cudaMemcpy(A.data(), G.js.A, sizeof(float4) * nj, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(B.data(), G.js.B, sizeof(float4) * nj, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(C.data(), G.js.C, sizeof(float4) * nj, cudaMemcpyDeviceToHost));
+    for (int j = 0; j < nj; j++) {
+        pos[j][0] = (double)A[j].x + (double)B[j].x;
+        pos[j][1] = (double)A[j].y + (double)B[j].y;
+        pos[j][2] = (double)A[j].z + (double)B[j].z;
+        vel[j][0] = C[j].x; vel[j][1] = C[j].y; vel[j][2] = C[j].z;
+    }
+    return 0;
+}
+
+double g6x_time_predictor(int nj, int reps)
+{
+    require_open("g6x_time_predictor");
+    flush_updates();
+    nj = std::min(nj, G.capacity);
+    if (nj <= 0 || reps <= 0) return 0.0;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    for (int r = 0; r < 3; r++) predict_kernel<<<(nj + 255) / 256, 256, 0, G.stream>>>(nj, G.ti, G.js);
+    CK(cudaEventRecord(e0, G.stream));
+    for (int r = 0; r < reps; r++) predict_kernel<<<(nj + 255) / 256, 256, 0, G.stream>>>(nj, G.ti, G.js);
+    CK(cudaEventRecord(e1, G.stream));
+    CK(cudaEventSynchronize(e1));
+    G.launches += reps + 3;
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return (double)ms / reps;
+}
+
+int g6x_set_variant(int variant)
+{
+    if (variant < 0 || variant >= V_COUNT) return -1;
+    G.variant = variant;
+    return 0;
+}
+
+double g6x_fp32_peak(int mode)
+{
+    require_open("g6x_fp32_peak");
+    float *d = nullptr;
+    dev_alloc(d, 256);
+    const int iters = 4096;
+    int blocks = G.sm_count * 8;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int r = 0; r < 6; r++) {
+        CK(cudaEventRecord(e0, G.stream));
+        if (mode == 0)
+            fp32_peak_kernel<0><<<blocks, 256, 0, G.stream>>>(d, iters, 1.0f);
+        else
+            fp32_peak_kernel<1><<<blocks, 256, 0, G.stream>>>(d, iters, 1.0f);
+        CK(cudaEventRecord(e1, G.stream));
+        CK(cudaEventSynchronize(e1));
+        float ms;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (r > 0) best = std::min(best, ms);
+        G.launches++;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    dev_free(d);
+    double fmas = (double)blocks * 256 * iters * 8 * 8 * (mode == 0 ? 1 : 2);
+    return 2.0 * fmas / (best * 1e-3) / 1e12;
+}
+
+}  // extern "C"

@@ -1,0 +1,681 @@
+// g6_kernels.cuh -- hand-written sm_100a kernels of the B200 g6 force library.
+//
+//   predict_kernel   j-particle Hermite predictor   (HBM-bound)
+//   scatter_kernel   j-update scatter               (HBM/latency-bound)
+//   pack_i_kernel    double -> double-single i-block packing (device callers)
+//   force_kernel<>   Hermite force: acc, jerk, pot, nearest neighbour,
+//                    neighbour-sphere lists         (FP32-issue-bound)
+//   resolve_nn_kernel  id lookup after a cross-rank min-reduction
+//
+// Reference behaviour being reproduced (not translated):
+//   force loop   src/amuse_ph4/src/idata.cc:198-236 (oracle, FP64)
+//   predictor    src/amuse_ph4/src/jdata.cc:726-747 (oracle, FP64)
+//   API/semantics lib/sapporo_light/dev_evaluate_gravity.cu:46-106 (DS positions,
+//                self-exclusion by id :76-79, neighbour rule :60-72)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace g6b {
+
+constexpr int THREADS = 256;   // threads per force CTA (8 warps)
+constexpr int TILE = 256;      // j-particles per shared-memory stage
+constexpr int STAGES = 3;      // TMA bulk-copy pipeline depth
+constexpr float TINYF = 2.220446049250313e-16f;  // 2^-52, stdinc.h:33
+constexpr float FAR_AWAY = 1.0e18f;  // where massless / unused j are parked
+constexpr unsigned long long KEY_NONE = 0x7f800000ffffffffULL;
+
+// ---------------------------------------------------------------------------
+// j state in HBM (capacity C, padded to a multiple of TILE):
+//   xy[C]  double2 (x, y)         zt[C]  double2 (z, t_j)
+//   vxy[C] double2 (vx, vy)       vz[C]  double
+//   am[C]  float4  (ax, ay, az, mass)    jk[C] float4 (jx, jy, jz, id bits)
+// predicted j (what the force kernel streams), float4 each:
+//   A = (x.hi, y.hi, z.hi, mass)  B = (x.lo, y.lo, z.lo, id bits)  C = (vx, vy, vz, 0)
+// ---------------------------------------------------------------------------
+struct JState {
+    double2 *xy, *zt, *vxy;
+    double *vz;
+    float4 *am, *jk;
+    float4 *A, *B, *C;
+};
+
+// One staged j-update (host pinned -> device staging -> scatter_kernel).
+struct __align__(16) JUpdate {
+    double x[3];
+    double v[3];
+    double t;
+    float a[3];
+    float j[3];
+    float m;
+    int id;
+    int addr;
+    int pad;
+};
+static_assert(sizeof(JUpdate) == 96, "JUpdate layout");
+
+__global__ void scatter_kernel(int n, const JUpdate *__restrict__ up, JState s)
+{
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    JUpdate u = up[k];
+    int a = u.addr;
+    s.xy[a] = make_double2(u.x[0], u.x[1]);
+    s.zt[a] = make_double2(u.x[2], u.t);
+    s.vxy[a] = make_double2(u.v[0], u.v[1]);
+    s.vz[a] = u.v[2];
+    s.am[a] = make_float4(u.a[0], u.a[1], u.a[2], u.m);
+    s.jk[a] = make_float4(u.j[0], u.j[1], u.j[2], __int_as_float(u.id));
+}
+
+// Hermite predictor (jdata.cc:726-747) in FP64, output split to double-single.
+// Algorithmic traffic: 88 B read + 48 B written per j.
+__global__ void predict_kernel(int n, double ti, JState s)
+{
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    double2 xy = s.xy[j], zt = s.zt[j], vxy = s.vxy[j];
+    double vz = s.vz[j];
+    float4 am = s.am[j], jk = s.jk[j];
+    double dt = ti - zt.y;
+    double h = 0.5 * dt, t3 = dt * (1.0 / 3.0);
+    double px = xy.x + dt * (vxy.x + h * ((double)am.x + t3 * (double)jk.x));
+    double py = xy.y + dt * (vxy.y + h * ((double)am.y + t3 * (double)jk.y));
+    double pz = zt.x + dt * (vz + h * ((double)am.z + t3 * (double)jk.z));
+    double qx = vxy.x + dt * ((double)am.x + h * (double)jk.x);
+    double qy = vxy.y + dt * ((double)am.y + h * (double)jk.y);
+    double qz = vz + dt * ((double)am.z + h * (double)jk.z);
+    if (!(am.w > TINYF)) {  // massless or never-set slot: park it (idata.cc:208)
+        px = py = pz = (double)FAR_AWAY;
+        qx = qy = qz = 0.0;
+    }
+    float xh = (float)px, yh = (float)py, zh = (float)pz;
+    float xl = (float)(px - (double)xh), yl = (float)(py - (double)yh), zl = (float)(pz - (double)zh);
+    s.A[j] = make_float4(xh, yh, zh, am.w);
+    s.B[j] = make_float4(xl, yl, zl, jk.w);
+    s.C[j] = make_float4((float)qx, (float)qy, (float)qz, 0.f);
+}
+
+// i-block packing for device-resident callers: double -> double-single.
+//   iA = (x.hi,y.hi,z.hi,h2)  iB = (x.lo,y.lo,z.lo,id bits)  iC = (vx,vy,vz,0)
+__global__ void pack_i_kernel(int ni, const int *__restrict__ index, const double *__restrict__ xi,
+                              const double *__restrict__ vi, const double *__restrict__ h2,
+                              float4 *iA, float4 *iB, float4 *iC)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ni) return;
+    double x = xi[3 * i], y = xi[3 * i + 1], z = xi[3 * i + 2];
+    float xh = (float)x, yh = (float)y, zh = (float)z;
+    iA[i] = make_float4(xh, yh, zh, h2 ? (float)h2[i] : 0.f);
+    iB[i] = make_float4((float)(x - (double)xh), (float)(y - (double)yh), (float)(z - (double)zh),
+                        __int_as_float(index[i]));
+    iC[i] = make_float4((float)vi[3 * i], (float)vi[3 * i + 1], (float)vi[3 * i + 2], 0.f);
+}
+
+// ---------------------------------------------------------------------------
+// PTX helpers: mbarrier + TMA 1-D bulk copy, packed f32x2 math, rsqrt.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t phase)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(phase)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ float rsqrt_approx(float x)
+{
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk(float lo, float hi)
+{
+    u64 d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+    return d;
+}
+__device__ __forceinline__ void upk(u64 v, float &lo, float &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ u64 add2(u64 a, u64 b)
+{
+    u64 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ u64 mul2(u64 a, u64 b)
+{
+    u64 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c)
+{
+    u64 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
+// ---------------------------------------------------------------------------
+// Force kernel.
+// ---------------------------------------------------------------------------
+struct ForceArgs {
+    const float4 *jA, *jB, *jC;   // predicted j (device)
+    const float4 *iA, *iB, *iC;   // packed i-block (device)
+    int ni, nj;                   // i count, j prefix [0, nj)
+    int tiles_per_split, nsplit;  // j decomposition over blockIdx.x
+    int ni_pad;                   // stride of the partial workspace
+    int j_offset;                 // global address of local address 0
+    float eps2;
+    double *part_sum;             // [nsplit][ni_pad][7]
+    u64 *part_key;                // [nsplit][ni_pad]
+    unsigned int *tickets;        // [gridDim.y], zero between launches
+    double *out_sum;              // [ni][7]: acc xyz, jerk xyz, +sum m/r
+    u64 *out_key;                 // [ni]
+    int *out_nnid;                // [ni]
+    int *ngb_cnt;                 // [ni]   (LIST only; zeroed by the host)
+    int *ngb_list;                // [ni][ngb_cap]
+    int ngb_cap;
+};
+
+struct Acc7 {
+    float ax, ay, az, jx, jy, jz, pot;
+};
+
+// One (i, j) interaction in scalar FP32 with double-single positions.
+// 9 FADD (DS dx) + 3 FADD (dv) + 6 FMUL/FFMA (r2, xv) + 1 FADD (eps2) + MUFU.RSQ
+// + 5 FMUL + 9 FFMA + 1 FADD, plus guards.  Counted as 60 flop by convention
+// (src/amuse_ph4/src/jdata.cc:1038).
+template <bool NN, bool LIST>
+__device__ __forceinline__ void interact(const float4 a, const float4 b, const float4 c, int jaddr, float xh,
+                                         float yh, float zh, float xl, float yl, float zl, float vx, float vy,
+                                         float vz, int iid, float h2, float eps2, Acc7 &s, float &r2min,
+                                         int &jmin, int i_global, const ForceArgs &p)
+{
+    float dx = (a.x - xh) + (b.x - xl);
+    float dy = (a.y - yh) + (b.y - yl);
+    float dz = (a.z - zh) + (b.z - zl);
+    float dvx = c.x - vx, dvy = c.y - vy, dvz = c.z - vz;
+    float r2 = dx * dx + dy * dy + dz * dz;
+    float xv = dx * dvx + dy * dvy + dz * dvz;
+    bool ok = (__float_as_int(b.w) != iid) && (r2 > TINYF);
+    float rinv = ok ? rsqrt_approx(r2 + eps2) : 0.f;
+    float rinv2 = rinv * rinv;
+    float mrinv = a.w * rinv;
+    float mr3 = mrinv * rinv2;
+    float a3 = -3.f * (xv * rinv2);
+    s.ax = fmaf(mr3, dx, s.ax);
+    s.ay = fmaf(mr3, dy, s.ay);
+    s.az = fmaf(mr3, dz, s.az);
+    s.jx = fmaf(mr3, fmaf(a3, dx, dvx), s.jx);
+    s.jy = fmaf(mr3, fmaf(a3, dy, dvy), s.jy);
+    s.jz = fmaf(mr3, fmaf(a3, dz, dvz), s.jz);
+    s.pot += mrinv;
+    if (NN) {
+        float r2n = ok ? r2 : __int_as_float(0x7f800000);
+        if (r2n < r2min) {
+            r2min = r2n;
+            jmin = jaddr;
+        }
+    }
+    if (LIST) {
+        if (ok && r2 <= h2) {
+            int pos = atomicAdd(&p.ngb_cnt[i_global], 1);
+            if (pos < p.ngb_cap) p.ngb_list[(size_t)i_global * p.ngb_cap + pos] = __float_as_int(b.w);
+        }
+    }
+}
+
+// Two i-particles at once with Blackwell's packed FP32 pipe (FADD2/FMUL2/FFMA2):
+// halves of every 64-bit register hold i0 and i1, the j operand is broadcast.
+// nX* hold NEGATED i coordinates so that differences are single FADD2s.
+struct IPair {
+    u64 nxh, nyh, nzh, nxl, nyl, nzl, nvx, nvy, nvz;
+    int id0, id1;
+    float h20, h21;
+};
+struct Acc7P {
+    u64 ax, ay, az, jx, jy, jz, pot;
+};
+
+template <bool NN, bool LIST>
+__device__ __forceinline__ void interact2(const float4 a, const float4 b, const float4 c, int jaddr, const IPair &I,
+                                          u64 eps2p, Acc7P &s, float &r2min0, int &jmin0, float &r2min1,
+                                          int &jmin1, int i_global0, const ForceArgs &p)
+{
+    u64 dx = add2(add2(pk(a.x, a.x), I.nxh), add2(pk(b.x, b.x), I.nxl));
+    u64 dy = add2(add2(pk(a.y, a.y), I.nyh), add2(pk(b.y, b.y), I.nyl));
+    u64 dz = add2(add2(pk(a.z, a.z), I.nzh), add2(pk(b.z, b.z), I.nzl));
+    u64 dvx = add2(pk(c.x, c.x), I.nvx);
+    u64 dvy = add2(pk(c.y, c.y), I.nvy);
+    u64 dvz = add2(pk(c.z, c.z), I.nvz);
+    u64 r2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
+    u64 xv = fma2(dz, dvz, fma2(dy, dvy, mul2(dx, dvx)));
+    u64 r2e = add2(r2, eps2p);
+    float r20, r21, e0, e1;
+    upk(r2, r20, r21);
+    upk(r2e, e0, e1);
+    int jid = __float_as_int(b.w);
+    bool ok0 = (jid != I.id0) && (r20 > TINYF);
+    bool ok1 = (jid != I.id1) && (r21 > TINYF);
+    float ri0 = ok0 ? rsqrt_approx(e0) : 0.f;
+    float ri1 = ok1 ? rsqrt_approx(e1) : 0.f;
+    u64 rinv = pk(ri0, ri1);
+    u64 rinv2 = mul2(rinv, rinv);
+    u64 mrinv = mul2(pk(a.w, a.w), rinv);
+    u64 mr3 = mul2(mrinv, rinv2);
+    u64 a3 = mul2(mul2(xv, rinv2), pk(-3.f, -3.f));
+    s.ax = fma2(mr3, dx, s.ax);
+    s.ay = fma2(mr3, dy, s.ay);
+    s.az = fma2(mr3, dz, s.az);
+    s.jx = fma2(mr3, fma2(a3, dx, dvx), s.jx);
+    s.jy = fma2(mr3, fma2(a3, dy, dvy), s.jy);
+    s.jz = fma2(mr3, fma2(a3, dz, dvz), s.jz);
+    s.pot = add2(s.pot, mrinv);
+    if (NN) {
+        float n0 = ok0 ? r20 : __int_as_float(0x7f800000);
+        float n1 = ok1 ? r21 : __int_as_float(0x7f800000);
+        if (n0 < r2min0) {
+            r2min0 = n0;
+            jmin0 = jaddr;
+        }
+        if (n1 < r2min1) {
+            r2min1 = n1;
+            jmin1 = jaddr;
+        }
+    }
+    if (LIST) {
+        if (ok0 && r20 <= I.h20) {
+            int pos = atomicAdd(&p.ngb_cnt[i_global0], 1);
+            if (pos < p.ngb_cap) p.ngb_list[(size_t)i_global0 * p.ngb_cap + pos] = jid;
+        }
+        if (ok1 && r21 <= I.h21) {
+            int pos = atomicAdd(&p.ngb_cnt[i_global0 + 1], 1);
+            if (pos < p.ngb_cap) p.ngb_list[(size_t)(i_global0 + 1) * p.ngb_cap + pos] = jid;
+        }
+    }
+}
+
+struct __align__(16) ForceSmem {
+    float4 A[STAGES][TILE];
+    float4 B[STAGES][TILE];
+    float4 C[STAGES][TILE];
+    uint64_t full[STAGES];
+    unsigned int is_last;
+};
+
+__device__ __forceinline__ u64 make_key(float r2min, int jmin_global)
+{
+    return ((u64)(unsigned)__float_as_int(r2min) << 32) | (u64)(unsigned)jmin_global;
+}
+
+// Thread layout: tid = jslot * NI_SLOTS + islot.  A CTA owns IB = NI_SLOTS*IPT
+// i-particles (i = blockIdx.y*IB + islot + k*NI_SLOTS, coalesced) and the j-tiles
+// of split blockIdx.x; inside a tile the NJ_SLOTS = THREADS/NI_SLOTS j-slots take
+// interleaved j.  i-particles stay in registers for the whole kernel; j tiles
+// arrive by TMA bulk copies (3 per stage) signalled on an mbarrier; per-tile FP32
+// partial sums are flushed to FP64 so that long sums keep ~1e-7 accuracy.
+// Partials of the j-slots are reduced with warp shuffles + shared memory, and the
+// partials of the j-splits by the last CTA to arrive (ticket), in fixed order.
+template <int IPT, int NI_SLOTS, bool NN, bool LIST, bool PACKED, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) force_kernel(const ForceArgs p)
+{
+    constexpr int NJ_SLOTS = THREADS / NI_SLOTS;
+    constexpr int IB = NI_SLOTS * IPT;
+    constexpr int LANES_PER_I = (NI_SLOTS >= 32) ? 1 : 32 / NI_SLOTS;   // lanes of a warp sharing an i
+    constexpr int JG = (NI_SLOTS >= 32) ? NJ_SLOTS : THREADS / 32;      // j-groups left after the shuffle stage
+    static_assert(!PACKED || (IPT % 2 == 0), "packed path handles i in pairs");
+    static_assert(JG * IB * 64 <= (int)sizeof(float4) * 3 * STAGES * TILE || JG == 1, "reduction scratch fits tile smem");
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    ForceSmem &sm = *reinterpret_cast<ForceSmem *>(smem_raw);
+
+    const int tid = threadIdx.x;
+    const int islot = tid % NI_SLOTS;
+    const int jslot = tid / NI_SLOTS;
+    const int i_base = blockIdx.y * IB + islot;
+
+    // ---- j tiles of this split -------------------------------------------
+    const int ntiles_total = (p.nj + TILE - 1) / TILE;
+    const int tile0 = blockIdx.x * p.tiles_per_split;
+    int ntiles = ntiles_total - tile0;
+    if (ntiles > p.tiles_per_split) ntiles = p.tiles_per_split;
+    if (ntiles < 0) ntiles = 0;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; s++) mbar_init(&sm.full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    constexpr uint32_t STAGE_BYTES = 3u * TILE * sizeof(float4);
+    if (tid == 0) {
+        for (int s = 0; s < STAGES && s < ntiles; s++) {
+            size_t off = (size_t)(tile0 + s) * TILE;
+            mbar_expect_tx(&sm.full[s], STAGE_BYTES);
+            bulk_g2s(sm.A[s], p.jA + off, TILE * sizeof(float4), &sm.full[s]);
+            bulk_g2s(sm.B[s], p.jB + off, TILE * sizeof(float4), &sm.full[s]);
+            bulk_g2s(sm.C[s], p.jC + off, TILE * sizeof(float4), &sm.full[s]);
+        }
+    }
+
+    // ---- register-resident i-particles -----------------------------------
+    float xh[IPT], yh[IPT], zh[IPT], xl[IPT], yl[IPT], zl[IPT], vx[IPT], vy[IPT], vz[IPT], h2[IPT];
+    int iid[IPT];
+#pragma unroll
+    for (int k = 0; k < IPT; k++) {
+        int i = i_base + k * NI_SLOTS;
+        if (PACKED) i = blockIdx.y * IB + (islot * 2 + (k & 1)) + (k >> 1) * (2 * NI_SLOTS);
+        float4 a = make_float4(0.f, 0.f, 0.f, -1.f), b = make_float4(0.f, 0.f, 0.f, __int_as_float(0x80000000)),
+               c = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < p.ni) {
+            a = p.iA[i];
+            b = p.iB[i];
+            c = p.iC[i];
+        }
+        xh[k] = a.x; yh[k] = a.y; zh[k] = a.z; h2[k] = a.w;
+        xl[k] = b.x; yl[k] = b.y; zl[k] = b.z; iid[k] = __float_as_int(b.w);
+        vx[k] = c.x; vy[k] = c.y; vz[k] = c.z;
+    }
+    auto i_of = [&](int k) -> int {
+        return PACKED ? (int)(blockIdx.y * IB + (islot * 2 + (k & 1)) + (k >> 1) * (2 * NI_SLOTS)) : i_base + k * NI_SLOTS;
+    };
+
+    double D[IPT][7];
+    float r2min[IPT];
+    int jmin[IPT];
+#pragma unroll
+    for (int k = 0; k < IPT; k++) {
+#pragma unroll
+        for (int q = 0; q < 7; q++) D[k][q] = 0.0;
+        r2min[k] = __int_as_float(0x7f800000);
+        jmin[k] = -1;
+    }
+
+    constexpr int NP = PACKED ? IPT / 2 : 1;
+    IPair IP[NP];
+    if (PACKED) {
+#pragma unroll
+        for (int q = 0; q < NP; q++) {
+            IP[q].nxh = pk(-xh[2 * q], -xh[2 * q + 1]);
+            IP[q].nyh = pk(-yh[2 * q], -yh[2 * q + 1]);
+            IP[q].nzh = pk(-zh[2 * q], -zh[2 * q + 1]);
+            IP[q].nxl = pk(-xl[2 * q], -xl[2 * q + 1]);
+            IP[q].nyl = pk(-yl[2 * q], -yl[2 * q + 1]);
+            IP[q].nzl = pk(-zl[2 * q], -zl[2 * q + 1]);
+            IP[q].nvx = pk(-vx[2 * q], -vx[2 * q + 1]);
+            IP[q].nvy = pk(-vy[2 * q], -vy[2 * q + 1]);
+            IP[q].nvz = pk(-vz[2 * q], -vz[2 * q + 1]);
+            IP[q].id0 = iid[2 * q];
+            IP[q].id1 = iid[2 * q + 1];
+            IP[q].h20 = h2[2 * q];
+            IP[q].h21 = h2[2 * q + 1];
+        }
+    }
+    const float eps2 = p.eps2;
+    const u64 eps2p = pk(eps2, eps2);
+
+    // ---- main loop over tiles --------------------------------------------
+    for (int t = 0; t < ntiles; t++) {
+        const int s = t % STAGES;
+        const uint32_t phase = (uint32_t)(t / STAGES) & 1u;
+        while (!mbar_try_wait(&sm.full[s], phase)) {
+        }
+        const int jtile = (tile0 + t) * TILE;
+        int cnt = p.nj - jtile;
+        if (cnt > TILE) cnt = TILE;
+        const float4 *tA = sm.A[s], *tB = sm.B[s], *tC = sm.C[s];
+
+        if (!PACKED) {
+            Acc7 S[IPT];
+#pragma unroll
+            for (int k = 0; k < IPT; k++) S[k] = Acc7{0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
+            for (int jj = jslot; jj < cnt; jj += NJ_SLOTS) {
+                const float4 a = tA[jj], b = tB[jj], c = tC[jj];
+                const int jaddr = jtile + jj;
+#pragma unroll
+                for (int k = 0; k < IPT; k++)
+                    interact<NN, LIST>(a, b, c, jaddr, xh[k], yh[k], zh[k], xl[k], yl[k], zl[k], vx[k], vy[k], vz[k],
+                                       iid[k], h2[k], eps2, S[k], r2min[k], jmin[k], i_of(k), p);
+            }
+#pragma unroll
+            for (int k = 0; k < IPT; k++) {
+                D[k][0] += (double)S[k].ax; D[k][1] += (double)S[k].ay; D[k][2] += (double)S[k].az;
+                D[k][3] += (double)S[k].jx; D[k][4] += (double)S[k].jy; D[k][5] += (double)S[k].jz;
+                D[k][6] += (double)S[k].pot;
+            }
+        } else {
+            Acc7P S[NP];
+#pragma unroll
+            for (int q = 0; q < NP; q++) S[q] = Acc7P{0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull};
+#pragma unroll 2
+            for (int jj = jslot; jj < cnt; jj += NJ_SLOTS) {
+                const float4 a = tA[jj], b = tB[jj], c = tC[jj];
+                const int jaddr = jtile + jj;
+#pragma unroll
+                for (int q = 0; q < NP; q++)
+                    interact2<NN, LIST>(a, b, c, jaddr, IP[q], eps2p, S[q], r2min[2 * q], jmin[2 * q],
+                                        r2min[2 * q + 1], jmin[2 * q + 1], i_of(2 * q), p);
+            }
+#pragma unroll
+            for (int q = 0; q < NP; q++) {
+                float lo, hi;
+                upk(S[q].ax, lo, hi); D[2 * q][0] += (double)lo; D[2 * q + 1][0] += (double)hi;
+                upk(S[q].ay, lo, hi); D[2 * q][1] += (double)lo; D[2 * q + 1][1] += (double)hi;
+                upk(S[q].az, lo, hi); D[2 * q][2] += (double)lo; D[2 * q + 1][2] += (double)hi;
+                upk(S[q].jx, lo, hi); D[2 * q][3] += (double)lo; D[2 * q + 1][3] += (double)hi;
+                upk(S[q].jy, lo, hi); D[2 * q][4] += (double)lo; D[2 * q + 1][4] += (double)hi;
+                upk(S[q].jz, lo, hi); D[2 * q][5] += (double)lo; D[2 * q + 1][5] += (double)hi;
+                upk(S[q].pot, lo, hi); D[2 * q][6] += (double)lo; D[2 * q + 1][6] += (double)hi;
+            }
+        }
+
+        __syncthreads();  // everyone is done with stage s
+        if (tid == 0 && t + STAGES < ntiles) {
+            size_t off = (size_t)(tile0 + t + STAGES) * TILE;
+            mbar_expect_tx(&sm.full[s], STAGE_BYTES);
+            bulk_g2s(sm.A[s], p.jA + off, TILE * sizeof(float4), &sm.full[s]);
+            bulk_g2s(sm.B[s], p.jB + off, TILE * sizeof(float4), &sm.full[s]);
+            bulk_g2s(sm.C[s], p.jC + off, TILE * sizeof(float4), &sm.full[s]);
+        }
+    }
+
+    // ---- keys ---------------------------------------------------------------
+    u64 key[IPT];
+#pragma unroll
+    for (int k = 0; k < IPT; k++)
+        key[k] = (jmin[k] >= 0) ? make_key(r2min[k], jmin[k] + p.j_offset) : KEY_NONE;
+
+    // ---- reduce over the j-slots of this CTA -------------------------------
+    double *red = reinterpret_cast<double *>(smem_raw);  // tile buffers are dead now
+    if (NJ_SLOTS > 1) {
+        if (LANES_PER_I > 1) {
+#pragma unroll
+            for (int off = NI_SLOTS; off < 32; off <<= 1) {
+#pragma unroll
+                for (int k = 0; k < IPT; k++) {
+#pragma unroll
+                    for (int q = 0; q < 7; q++) D[k][q] += __shfl_xor_sync(0xffffffffu, D[k][q], off);
+                    u64 o = __shfl_xor_sync(0xffffffffu, key[k], off);
+                    key[k] = o < key[k] ? o : key[k];
+                }
+            }
+        }
+        __syncthreads();  // all warps past their last tile reads (also covers ntiles == 0)
+        const int g = (NI_SLOTS >= 32) ? jslot : (tid >> 5);
+        const bool writer = (NI_SLOTS >= 32) ? true : ((tid & 31) < NI_SLOTS);
+        if (writer) {
+#pragma unroll
+            for (int k = 0; k < IPT; k++) {
+                int il = PACKED ? (islot * 2 + (k & 1)) + (k >> 1) * (2 * NI_SLOTS) : islot + k * NI_SLOTS;
+                double *r = red + ((size_t)g * IB + il) * 8;
+#pragma unroll
+                for (int q = 0; q < 7; q++) r[q] = D[k][q];
+                reinterpret_cast<u64 *>(r)[7] = key[k];
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- CTA totals -> global (final or per-split partial) ------------------
+    const bool single = (p.nsplit == 1);
+    auto emit = [&](int il, const double *tot, u64 kk) {
+        int i = blockIdx.y * IB + il;
+        if (i >= p.ni) return;
+        if (single) {
+#pragma unroll
+            for (int q = 0; q < 7; q++) p.out_sum[(size_t)i * 7 + q] = tot[q];
+            p.out_key[i] = kk;
+            if (NN) {
+                int id = -1;
+                if (kk != KEY_NONE) id = __float_as_int(p.jB[(int)(unsigned)(kk & 0xffffffffu) - p.j_offset].w);
+                p.out_nnid[i] = id;
+            }
+        } else {
+            size_t o = (size_t)blockIdx.x * p.ni_pad + i;
+#pragma unroll
+            for (int q = 0; q < 7; q++) p.part_sum[o * 7 + q] = tot[q];
+            p.part_key[o] = kk;
+        }
+    };
+    if (NJ_SLOTS > 1) {
+        for (int il = tid; il < IB; il += THREADS) {
+            double tot[7] = {0, 0, 0, 0, 0, 0, 0};
+            u64 kk = KEY_NONE;
+            for (int g = 0; g < JG; g++) {
+                const double *r = red + ((size_t)g * IB + il) * 8;
+#pragma unroll
+                for (int q = 0; q < 7; q++) tot[q] += r[q];
+                u64 o = reinterpret_cast<const u64 *>(r)[7];
+                kk = o < kk ? o : kk;
+            }
+            emit(il, tot, kk);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < IPT; k++) {
+            int il = PACKED ? (islot * 2 + (k & 1)) + (k >> 1) * (2 * NI_SLOTS) : islot + k * NI_SLOTS;
+            emit(il, D[k], key[k]);
+        }
+    }
+    if (single) return;
+
+    // ---- last CTA of this i-block sums the splits in fixed order ------------
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        unsigned int tk = atomicAdd(&p.tickets[blockIdx.y], 1u);
+        sm.is_last = (tk == (unsigned)p.nsplit - 1u) ? 1u : 0u;
+        if (sm.is_last) p.tickets[blockIdx.y] = 0u;  // ready for the next launch
+    }
+    __syncthreads();
+    if (!sm.is_last) return;
+    __threadfence();
+    for (int il = tid; il < IB; il += THREADS) {
+        int i = blockIdx.y * IB + il;
+        if (i >= p.ni) continue;
+        double tot[7] = {0, 0, 0, 0, 0, 0, 0};
+        u64 kk = KEY_NONE;
+        for (int sp = 0; sp < p.nsplit; sp++) {
+            size_t o = (size_t)sp * p.ni_pad + i;
+            const double *r = p.part_sum + o * 7;
+#pragma unroll
+            for (int q = 0; q < 7; q++) tot[q] += __ldcg(r + q);
+            u64 ok = __ldcg(p.part_key + o);
+            kk = ok < kk ? ok : kk;
+        }
+#pragma unroll
+        for (int q = 0; q < 7; q++) p.out_sum[(size_t)i * 7 + q] = tot[q];
+        p.out_key[i] = kk;
+        if (NN) {
+            int id = -1;
+            if (kk != KEY_NONE) id = __float_as_int(p.jB[(int)(unsigned)(kk & 0xffffffffu) - p.j_offset].w);
+            p.out_nnid[i] = id;
+        }
+    }
+}
+
+// After a min-reduction of keys over ranks (each rank holds a j-shard).
+__global__ void resolve_nn_kernel(int ni, const u64 *__restrict__ key, int rank, int j_offset, int nj_local,
+                                  const float4 *__restrict__ jB, int *nnid)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ni) return;
+    u64 k = key[i];
+    int id = 0;
+    if (k == KEY_NONE) {
+        id = (rank == 0) ? -1 : 0;
+    } else {
+        int a = (int)(unsigned)(k & 0xffffffffu) - j_offset;
+        if (a >= 0 && a < nj_local) id = __float_as_int(jB[a].w);
+    }
+    nnid[i] = id;
+}
+
+// ---------------------------------------------------------------------------
+// FP32 pipe microbenchmark (roofline denominator measured on the device).
+// ---------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(256) fp32_peak_kernel(float *out, int iters, float seed)
+{
+    constexpr int CH = 8;
+    if (MODE == 0) {
+        float x[CH];
+#pragma unroll
+        for (int c = 0; c < CH; c++) x[c] = seed + threadIdx.x * 1e-6f + c;
+        float m = 0.999999f, a = 1e-7f + seed;
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+#pragma unroll
+                for (int c = 0; c < CH; c++) x[c] = fmaf(x[c], m, a);
+        }
+        float s = 0;
+#pragma unroll
+        for (int c = 0; c < CH; c++) s += x[c];
+        if (s == 12345.678f) out[threadIdx.x] = s;
+    } else {
+        u64 x[CH];
+#pragma unroll
+        for (int c = 0; c < CH; c++) x[c] = pk(seed + threadIdx.x * 1e-6f + c, seed + c + 0.5f);
+        u64 m = pk(0.999999f, 0.999998f), a = pk(1e-7f + seed, 2e-7f + seed);
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+#pragma unroll
+                for (int c = 0; c < CH; c++) x[c] = fma2(x[c], m, a);
+        }
+        float s = 0;
+#pragma unroll
+        for (int c = 0; c < CH; c++) {
+            float lo, hi;
+            upk(x[c], lo, hi);
+            s += lo + hi;
+        }
+        if (s == 12345.678f) out[threadIdx.x] = s;
+    }
+}
+
+}  // namespace g6b

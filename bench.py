@@ -1,0 +1,389 @@
+#!/usr/bin/env python
+"""Benchmark of the g6 Hermite force path (BASELINE.json metric: interactions/s and % of FP32
+peak for full i-block force sweeps on synthetic Plummer spheres, headline N = 1M).
+
+    python bench.py --gpus N --steps K --warmup W            # this library on N B200s
+    python bench.py --impl reference --gpus N ...            # the reference CPU path (rank 0)
+
+One "step" = one full i-block force sweep: predict all j to t, then acc/jerk/pot/nearest
+neighbour of all N i-particles against all N j-particles (N^2 interactions).
+
+* value : device-timed (CUDA events on the launching stream), inputs resident in HBM,
+          j sharded over the ranks, partial forces combined by an NCCL all-reduce
+          (sum acc/jerk/pot, min nearest-neighbour key, sum of resolved ids).
+* e2e   : N=1: the same sweep through the g6 C ABI with HOST buffers (g6_set_ti_, then
+          g6calc_firsthalf_/g6calc_lasthalf2_ per 16384-particle chunk; H2D/D2H inside).
+          N>1: pinned host inputs -> H2D -> device entry point -> all-reduce -> D2H.
+* roofline : FP32 pipe, 60 flop/interaction convention (src/amuse_ph4/src/jdata.cc:1038).
+* cpu_baseline : the reference's own double-precision force loop (oracle/_ref, built from the
+          unmodified ph4 sources) or the oracle port, timed on this box's host cores on a bounded
+          i-sample of the same workload.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FLOP_PER_INTERACTION = 60.0          # convention, src/amuse_ph4/src/jdata.cc:1038
+NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12   # SMs x FP32 lanes x 2 x clocks.max.sm (B200_PROFILING.md)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=1 << 20, help="particles (default 1M, the headline size)")
+    ap.add_argument("--eps2", type=float, default=0.0)
+    ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--variant", type=int, default=0)
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm (reference): ph4's own force loop on the host cores.
+# ------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    """Seconds spent in the reference force loop itself (setup of the reference's jdata excluded)."""
+    kind, mass, pos, vel, eps2, lo, hi = args
+    from oracle import oracle as O
+    if kind == "reference":
+        n = len(mass)
+        z = np.zeros((n, 3))
+        r = O.ref_predict_force(mass, np.zeros(n), pos, vel, z, z, 0.0, eps2, pos[lo:hi], vel[lo:hi])
+        return r["seconds"]
+    t0 = time.perf_counter()
+    O.force(pos[lo:hi], vel[lo:hi], mass, pos, vel, eps2)
+    return time.perf_counter() - t0
+
+
+def cpu_rate(mass, pos, vel, eps2, ni_total, procs):
+    """interactions/s of the reference CPU loop: ni_total sampled i x all j, split over `procs`
+    processes (ph4 itself is single-threaded; its parallel mode is one MPI rank per core)."""
+    import multiprocessing as mp
+    from oracle import oracle as O
+    kind = "reference" if O.ref_available() else "port"
+    n = len(mass)
+    per = max(1, ni_total // procs)
+    jobs = [(kind, mass, pos, vel, eps2, k * per, (k + 1) * per) for k in range(procs)]
+    if procs == 1:
+        secs = [_cpu_worker(jobs[0])]
+    else:
+        with mp.get_context("fork").Pool(procs) as pool:
+            secs = pool.map(_cpu_worker, jobs)
+    dt = max(secs)
+    return per * procs * float(n) / dt, kind, per * procs, dt
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from amuse_b200 import plummer as P
+    n = a.n
+    mass, pos, vel = P.new_plummer_model(n, seed=a.seed)
+    cores = os.cpu_count() or 1
+    # size the sample so that one step is ~cpu_seconds/steps of work at ~5e7 interactions/s/core
+    per_step_s = max(2.0, min(20.0, 60.0 / max(1, a.steps + a.warmup)))
+    ni = int(max(cores, min(n, 5.0e7 * cores * per_step_s / n)))
+    ni = max(cores, (ni // cores) * cores)
+    for _ in range(a.warmup):
+        cpu_rate(mass, pos, vel, a.eps2, max(cores, ni // 8), cores)
+    rates = []
+    t_tot = 0.0
+    kind = "port"
+    for _ in range(a.steps):
+        r, kind, ni_used, dt = cpu_rate(mass, pos, vel, a.eps2, ni, cores)
+        rates.append(r)
+        t_tot += dt
+    value = float(np.mean(rates))
+    sample = "%d sampled i x %d j per step (%.1f%% of one N^2 sweep), %d processes" % (ni, n, 100.0 * ni / n, cores)
+    line = {
+        "impl": "reference", "metric": "interactions/s", "value": value, "unit": "interactions/s",
+        "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * t_tot / max(1, a.steps),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "full i-block Hermite force sweep, Plummer N=%d, eps2=%g (sampled on CPU)" % (n, a.eps2),
+                   "n": n, "eps2": a.eps2},
+        "cpu_baseline": {"value": value, "unit": "interactions/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "interactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append((time.perf_counter(), ln.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, smax, reasons, power = [], None, set(), []
+        for t, ln in self.lines:
+            f = [s.strip() for s in ln.split(",")]
+            if len(f) < 9 or not (t0 <= t <= t1 + 0.3):
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax = float(f[2])
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def run_b200(a):
+    import torch
+    import torch.distributed as dist
+    from amuse_b200 import g6lib, plummer as P
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != a.gpus:
+        if world == 1 and a.gpus > 1:
+            raise SystemExit("bench.py --gpus %d must be launched with torch.distributed.run (one rank per GPU)" % a.gpus)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- this library has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    n = a.n
+    mass, pos, vel = P.new_plummer_model(n, seed=a.seed)      # identical on every rank
+    ids = np.arange(1, n + 1, dtype=np.int32)
+    # j-domain of this rank: jdata::define_domain (src/amuse_ph4/src/jdata.cc:56-67)
+    per = (n + world - 1) // world
+    j0, j1 = rank * per, min(n, (rank + 1) * per)
+    g = g6lib.G6(local)
+    L = g.L
+    L.g6x_set_stream(C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+    L.g6x_set_j_offset(j0)
+    if a.variant:
+        g.set_variant(a.variant)
+    g.set_j_particles(ids[j0:j1], mass[j0:j1], pos[j0:j1], vel[j0:j1])
+    njl = j1 - j0
+    npipes = g.npipes
+
+    # device-resident i-block (all N particles; replicated on every rank like ph4's i-list)
+    h_id = torch.from_numpy(ids).pin_memory()
+    h_x = torch.from_numpy(pos).pin_memory()
+    h_v = torch.from_numpy(vel).pin_memory()
+    d_id, d_x, d_v = h_id.to(dev), h_x.to(dev), h_v.to(dev)
+    d_sum = torch.empty((n, 7), dtype=torch.float64, device=dev)
+    d_key = torch.empty(n, dtype=torch.int64, device=dev)
+    d_nn = torch.empty(n, dtype=torch.int32, device=dev)
+    h_sum = torch.empty((n, 7), dtype=torch.float64).pin_memory()
+    h_nn = torch.empty(n, dtype=torch.int32).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    chunk_events = []
+
+    def sweep(t, record=False):
+        """predict + force sweep + cross-rank reduction; everything on the current stream."""
+        L.g6x_predict(njl, float(t))
+        for i0 in range(0, n, npipes):
+            ni = min(npipes, n - i0)
+            if record:
+                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                e0.record()
+            L.g6x_calc_device(njl, ni, d_id.data_ptr() + 4 * i0, d_x.data_ptr() + 24 * i0, d_v.data_ptr() + 24 * i0,
+                              None, a.eps2, 1, d_sum.data_ptr() + 56 * i0, d_key.data_ptr() + 8 * i0,
+                              d_nn.data_ptr() + 4 * i0)
+            if record:
+                e1.record()
+                chunk_events.append((e0, e1, ni))
+        if world > 1:
+            dist.all_reduce(d_sum, op=dist.ReduceOp.SUM)
+            dist.all_reduce(d_key, op=dist.ReduceOp.MIN)
+            L.g6x_resolve_nn(n, d_key.data_ptr(), rank, d_nn.data_ptr())
+            dist.all_reduce(d_nn, op=dist.ReduceOp.SUM)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for w in range(a.warmup):
+        flush.fill_(w)
+        sweep(0.0)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    launches0 = g.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    barrier()
+    t_wall0 = time.perf_counter()
+    for k in range(a.steps):
+        flush.fill_(k)            # evict j/i data from L2 between timed iterations
+        ev[k][0].record()
+        sweep(0.0, record=True)
+        ev[k][1].record()
+    barrier()
+    t_wall1 = time.perf_counter()
+    launches = g.launch_count() - launches0
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    ms_local = sum(e0.elapsed_time(e1) for e0, e1 in ev)
+    ms_t = torch.tensor([ms_local], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+    ms_total = float(ms_t.item())
+    ms_per_step = ms_total / a.steps
+    value = float(n) * float(n) / (ms_per_step * 1e-3)
+
+    # roofline of the dominant kernel (force_kernel): per-launch algorithmic flop / mean launch duration
+    kms = np.array([e0.elapsed_time(e1) for e0, e1, _ in chunk_events])
+    kni = np.array([ni for _, _, ni in chunk_events], dtype=np.float64)
+    flop_per_launch = FLOP_PER_INTERACTION * kni.mean() * njl
+    achieved = flop_per_launch / (kms.mean() * 1e-3) / 1e12
+    kernel_share = float(kms.sum() / ms_total)
+
+    # measured FP32 FMA pipe peak (dependent-chain FFMA / FFMA2 microbenchmarks in the library)
+    ffma = L.g6x_fp32_peak(0)
+    ffma2 = L.g6x_fp32_peak(1)
+    # predictor: HBM-bound kernel, 88 B read + 48 B written per j
+    pred_ms = L.g6x_time_predictor(njl, 20)
+    pred_gbs = 136.0 * njl / (pred_ms * 1e-3) / 1e9 if pred_ms > 0 else None
+
+    # ---- end-to-end through the public API with host buffers ------------------------------------
+    e2e = None
+    if not a.no_e2e:
+        e2e_steps = max(1, min(a.steps, 2))
+        if world == 1:
+            L.g6x_set_stream(None)
+            g.set_ti(0.0)
+            g.calc(ids[:npipes], pos[:npipes], vel[:npipes], a.eps2)      # warm the ABI path
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                g.set_ti(0.0)
+                out = g.calc(ids, pos, vel, a.eps2)
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) / e2e_steps
+            h2d, d2h = 48 * n, 60 * n
+            how = "g6 C ABI, host double arrays, %d-particle chunks" % npipes
+        else:
+            def e2e_step():
+                d_id.copy_(h_id, non_blocking=True)
+                d_x.copy_(h_x, non_blocking=True)
+                d_v.copy_(h_v, non_blocking=True)
+                sweep(0.0)
+                h_sum.copy_(d_sum, non_blocking=True)
+                h_nn.copy_(d_nn, non_blocking=True)
+            e2e_step()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                e2e_step()
+            barrier()
+            dt_t = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=dev)
+            dist.all_reduce(dt_t, op=dist.ReduceOp.MAX)
+            dt = float(dt_t.item())
+            h2d, d2h = (4 + 48) * n, 60 * n
+            how = "pinned host i-arrays -> H2D -> g6x_calc_device -> NCCL all-reduce -> D2H, per rank"
+        e2e = {"value": float(n) * float(n) / dt, "unit": "interactions/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "ms_per_step": dt * 1e3, "how": how}
+
+    # ---- CPU baseline on this box's host cores (rank 0, N=1 only) -------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        try:
+            ni_cpu = int(max(8, min(n, 5.0e7 * a.cpu_seconds / n)))
+            r, kind, ni_used, dtc = cpu_rate(mass, pos, vel, a.eps2, ni_cpu, 1)
+            cpu = {"value": r, "unit": "interactions/s", "cores": 1, "kind": kind,
+                   "sample": "%d sampled i x %d j (%.2f%% of one sweep), %.1f s, ph4 force loop idata.cc:147-237" % (
+                       ni_used, n, 100.0 * ni_used / n, dtc)}
+        except Exception as e:  # the checker is optional infrastructure; never the measured path
+            cpu = {"value": None, "unit": "interactions/s", "cores": 0, "kind": "unavailable", "sample": repr(e)}
+
+    g.close()
+    if rank == 0:
+        peak_src = "nominal 148 SM x 128 lanes x 2 x 1.965 GHz (MEASURED_PEAKS.json holds no FP32 figure); " \
+                   "measured FFMA microbenchmark alongside"
+        line = {
+            "metric": "interactions/s", "value": value, "unit": "interactions/s", "n_gpus": world,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32 (double-single positions, f64 reduction)",
+            "data": "synthetic",
+            "config": {"workload": "full i-block Hermite force sweep (acc, jerk, pot, nearest neighbour), "
+                                   "Plummer N=%d, eps2=%g, i-chunks of %d, j sharded over %d GPU(s)" % (
+                                       n, a.eps2, npipes, world),
+                       "n": n, "eps2": a.eps2, "npipes": npipes, "l2": "256 MiB buffer written between timed steps",
+                       "parallelism": "j-shard x%d + all-reduce" % world},
+            "tflops_60": value * FLOP_PER_INTERACTION / 1e12,
+            "frac_fp32_peak_nominal": value * FLOP_PER_INTERACTION / 1e12 / (NOMINAL_FP32_TFLOPS * world),
+            "roofline": {"bound": "fp32", "achieved": achieved, "peak": NOMINAL_FP32_TFLOPS, "unit": "TFLOP/s",
+                         "frac": achieved / NOMINAL_FP32_TFLOPS, "traffic": None, "peak_source": peak_src,
+                         "kernel": "force_kernel", "flop_per_launch": flop_per_launch,
+                         "ms_per_launch": float(kms.mean()), "launches_timed": int(len(kms)),
+                         "kernel_share_of_step": kernel_share,
+                         "measured_ffma_tflops": ffma, "measured_ffma2_tflops": ffma2,
+                         "frac_of_measured_ffma": achieved / max(ffma, ffma2, 1e-9)},
+            "predictor": {"bound": "hbm", "achieved": pred_gbs, "unit": "GB/s", "bytes_per_j": 136,
+                          "ms_per_launch": pred_ms},
+            "e2e": e2e, "cpu_baseline": cpu, "gpu_launches": int(launches), "clocks": clocks,
+        }
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            if pred_gbs:
+                line["predictor"]["peak"] = peaks.get("hbm_gbs")
+                line["predictor"]["frac"] = pred_gbs / peaks.get("hbm_gbs")
+        except Exception:
+            pass
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)

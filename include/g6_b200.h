@@ -1,0 +1,191 @@
+/*
+ * g6_b200.h -- C ABI of the B200-native GRAPE-6/Sapporo force library.
+ *
+ * The library (libsapporo.so, alias libg6.so) is a drop-in for the two g6
+ * implementations AMUSE ships:
+ *     lib/sapporo_light/sapporoG6lib.cpp:5-81   (CUDA, 2008-era)
+ *     lib/g6lib/g6lib.h:8-128, g6lib.c:190-481  (CPU emulation)
+ * Callers that bind these symbols: src/amuse_ph4/src/grape.h:6-120 (ph4),
+ * src/amuse_phigrape/src/{initgrape,sendbodies2grape,update_grape,gravity}.F
+ * (phiGRAPE, Fortran: every argument by reference, trailing underscore),
+ * src/amuse_bhtree/src/BHtree.C:763-885.
+ *
+ * Part 1 declares exactly the symbols those callers link against.
+ * Part 2 ("g6x_") is the batched / device-resident extension used by the
+ * benchmark, the multi-GPU path and any caller that keeps data in HBM.
+ * Plain pointers and sizes only; no C++ or torch types cross this boundary.
+ */
+#ifndef G6_B200_H
+#define G6_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ======================================================================
+ * Part 1 -- the GRAPE-6 ABI (Fortran convention: trailing '_', all pointers)
+ * ====================================================================== */
+
+/* Open the device.  *id = CUDA device ordinal (ph4 passes its MPI rank or
+ * gpu_id, src/amuse_ph4/src/gpu.cc:56-59).  Returns 0, or -1 if no such
+ * device (lib/sapporo_light/sapporo.cpp:19-41).  Re-opening is allowed
+ * (phiGRAPE opens/closes around every evolve, interface.F:552-594). */
+int g6_open_(int *id);
+/* Free all device state (lib/sapporo_light/sapporo.cpp:43-56). */
+int g6_close_(int *id);
+/* Max i-particles per firsthalf/lasthalf call (sapporo_light: 256,
+ * sapporo.h:149; g6lib: 1).  Here 16384 (phiGRAPE's NGP bound,
+ * src/amuse_phigrape/src/gravity.F) unless env G6_B200_NPIPES overrides. */
+int g6_npipes_(void);
+/* Unit setters of the GRAPE hardware; ignored (sapporoG6lib.cpp:9-10).  ph4
+ * declares double*, phiGRAPE passes int*: the argument is never read. */
+int g6_set_tunit_(void *unused);
+int g6_set_xunit_(void *unused);
+/* Set the time all j-particles are predicted to by the next force call
+ * (sapporo.cpp:58-62). */
+int g6_set_ti_(int *id, double *ti);
+/* Store j-particle at slot *address (sapporo.cpp:68-112).  a2 = acc/2,
+ * j6 = jerk/6, k18 = snap/18 (ignored, as in sapporo.cpp:91-96).  *index is the
+ * particle id used for self-exclusion and returned as nearest neighbour.  The
+ * update becomes visible to the next g6calc_firsthalf_. */
+int g6_set_j_particle_(int *cluster_id, int *address, int *index, double *tj,
+                       double *dtj, double *mass, double k18[3], double j6[3],
+                       double a2[3], double v[3], double x[3]);
+/* Capture the i-block (ni <= g6_npipes_()) and start the device work for it:
+ * pending j-updates are uploaded, all j in [0,*nj) are predicted to ti, the
+ * i-block is uploaded (sapporo.cpp:114-152).  aold/j6old/phiold are GRAPE
+ * scaling hints and are ignored.  h2[i] = squared neighbour radius. */
+void g6calc_firsthalf_(int *cluster_id, int *nj, int *ni, int index[],
+                       double xi[][3], double vi[][3], double aold[][3],
+                       double j6old[][3], double phiold[], double *eps2,
+                       double h2[]);
+/* Finish the force evaluation of the captured i-block: acc, jerk and pot
+ * (negative: -sum m/sqrt(r2+eps2)) against j in [0,*nj)  (sapporo.cpp:154-181). */
+int g6calc_lasthalf_(int *cluster_id, int *nj, int *ni, int index[],
+                     double xi[][3], double vi[][3], double *eps2, double h2[],
+                     double acc[][3], double jerk[][3], double pot[]);
+/* Same, and also inn[i] = index (id) of the nearest j by unsoftened distance,
+ * self excluded (sapporo.cpp:184-232); -1 if there is none.  Also builds the
+ * neighbour-sphere lists (r2 <= h2[i]) when any h2[i] > 0. */
+int g6calc_lasthalf2_(int *cluster_id, int *nj, int *ni, int index[],
+                      double xi[][3], double vi[][3], double *eps2, double h2[],
+                      double acc[][3], double jerk[][3], double pot[],
+                      int inn[]);
+/* GRAPE buffer management: no-ops (sapporoG6lib.cpp:52-55). */
+int g6_initialize_jp_buffer_(int *cluster_id, int *buf_size);
+int g6_flush_jp_buffer_(int *cluster_id);
+int g6_reset_(int *cluster_id);
+int g6_reset_fofpga_(int *cluster_id);
+/* Fetch the neighbour lists of the last lasthalf2 to the host.  Returns
+ * non-zero iff any list overflowed the per-particle capacity
+ * (sapporo.cpp:234-246; capacity there 256, here G6_B200_NGB_CAP, default 1024). */
+int g6_read_neighbour_list_(int *cluster_id);
+/* Copy the list of i-particle *ipipe: ids with r2 <= h2, self excluded, sorted
+ * ascending; *n_neighbours = full count; returns non-zero iff the count does
+ * not fit in *maxlength (sapporo.cpp:248-272). */
+int g6_get_neighbour_list_(int *cluster_id, int *ipipe, int *maxlength,
+                           int *n_neighbours, int neighbour_list[]);
+/* Number of CUDA devices; the symbol AMUSE's configure probes for
+ * (support/shared/m4/amuse_lib.m4:135-137; lib/sapporo_light/send_fetch_data.cpp). */
+int get_device_count(void);
+
+/* By-value variants exported by lib/g6lib (g6lib.h:58-128) and probed by
+ * AC_SEARCH_LIBS(g6_npipes, g6) (amuse_lib.m4:126-128).  ph4 defines its own
+ * copies in grape.cc:7-146; the executable's definition wins. */
+int g6_open(int clusterid);
+int g6_close(int clusterid);
+int g6_npipes(void);
+int g6_set_tunit(int newtunit);
+int g6_set_xunit(int newxunit);
+int g6_set_ti(int clusterid, double ti);
+int g6_set_j_particle(int clusterid, int address, int index, double tj,
+                      double dtj, double mass, double a2by18[3],
+                      double a1by6[3], double aby2[3], double v[3], double x[3]);
+void g6calc_firsthalf(int clusterid, int nj, int ni, int index[],
+                      double xi[][3], double vi[][3], double fold[][3],
+                      double jold[][3], double phiold[], double eps2,
+                      double h2[]);
+int g6calc_lasthalf(int clusterid, int nj, int ni, int index[], double xi[][3],
+                    double vi[][3], double eps2, double h2[], double acc[][3],
+                    double jerk[][3], double pot[]);
+int g6calc_lasthalf2(int clusterid, int nj, int ni, int index[],
+                     double xi[][3], double vi[][3], double eps2, double h2[],
+                     double acc[][3], double jerk[][3], double pot[],
+                     int nnbindex[]);
+int g6_initialize_jp_buffer(int clusterid, int size);
+int g6_flush_jp_buffer(int clusterid);
+void g6_reset(int devid);
+int g6_reset_fofpga(int devid);
+void g6_reinitialize(int clusterid);
+int g6_get_number_of_pipelines(void);
+int g6_read_neighbour_list(int clusterid);
+int g6_get_neighbour_list(int clusterid, int ipipe, int maxlength, int *nblen,
+                          int nbl[]);
+void g6_set_neighbour_list_sort_mode(int mode);
+int g6_get_neighbour_list_sort_mode(void);
+/* Debug hooks ph4 declares (grape.h:110-119); harmless stubs. */
+int g6_set_overflow_flag_test_mode(int aflag, int jflag, int pflag);
+void force_j_particle_send(void);
+
+/* ======================================================================
+ * Part 2 -- g6x_: batched and device-resident entry points
+ * ====================================================================== */
+
+/* Library/ABI version (major*100 + minor). */
+int g6x_version(void);
+/* Use an externally owned CUDA stream (a cudaStream_t passed as void*) for all
+ * work; NULL restores the library's own stream. */
+int g6x_set_stream(void *cuda_stream);
+/* This process owns j-addresses whose GLOBAL address is local + offset (used
+ * when j is sharded over ranks; the offset is packed in the nearest-neighbour
+ * keys so a min-reduction over ranks is meaningful). */
+int g6x_set_j_offset(int offset);
+/* Array form of g6_set_j_particle_ for n particles (host arrays; k18 omitted).
+ * address == NULL means address[k] = address0 + k. */
+int g6x_set_j_particles(int n, const int *address, int address0,
+                        const int *index, const double *tj, const double *mass,
+                        const double (*j6)[3], const double (*a2)[3],
+                        const double (*v)[3], const double (*x)[3]);
+/* Upload pending j-updates and predict j in [0,nj) to ti now (asynchronous). */
+int g6x_predict(int nj, double ti);
+/* Device-resident force evaluation, asynchronous on the library stream.
+ * Inputs are DEVICE pointers: d_index[ni], d_xi[ni][3], d_vi[ni][3], d_h2[ni]
+ * (may be NULL = 0).  Outputs are DEVICE pointers: d_sum[ni][7] =
+ * (acc xyz, jerk xyz, +sum m/r), d_key[ni] = (float bits of min r2) << 32 |
+ * global j address (0x7f800000ffffffff if none), d_nnid[ni] = id of nearest j
+ * or -1 (valid for a single shard; see g6x_resolve_nn).
+ * flags: bit0 = nearest neighbour wanted, bit1 = neighbour lists wanted.
+ * Runs the predictor first if ti or any j changed.  ni is unlimited (the call
+ * loops over npipes-sized chunks).  Returns 0. */
+int g6x_calc_device(int nj, int ni, const int *d_index, const double *d_xi,
+                    const double *d_vi, const double *d_h2, double eps2,
+                    int flags, double *d_sum, unsigned long long *d_key,
+                    int *d_nnid);
+/* After a min-reduction of d_key over ranks: d_nnid[i] = id of the winning j if
+ * this rank owns it, else 0 (so a sum over ranks gives the id), -1 on rank 0
+ * if there is no neighbour.  Mirrors idata.cc:308-313. */
+int g6x_resolve_nn(int ni, const unsigned long long *d_key, int rank,
+                   int *d_nnid);
+/* Block until the library stream is idle. */
+int g6x_synchronize(void);
+/* Cumulative number of CUDA kernels this library has launched. */
+long long g6x_launch_count(void);
+/* Device pointers of the predicted j arrays (float4 each): A = (x.hi,y.hi,z.hi,m),
+ * B = (x.lo,y.lo,z.lo,id bits), C = (vx,vy,vz,0); for tests/inspection. */
+int g6x_get_predicted(void **A, void **B, void **C, int *capacity);
+/* Copy predicted j state back to the host as doubles (tests): pos = hi+lo. */
+int g6x_read_predicted(int nj, double (*pos)[3], double (*vel)[3]);
+/* Time only the j-predictor / j-update kernels (CUDA events, ms per launch,
+ * averaged over reps) for the HBM roofline of those kernels. */
+double g6x_time_predictor(int nj, int reps);
+/* Which force-kernel variant the next calls use: 0 = auto, else a fixed variant
+ * id; for benchmarking and tests. */
+int g6x_set_variant(int variant);
+/* FP32 pipe microbenchmark: returns achieved TFLOP/s (2 flop per FMA lane) of a
+ * dependent-chain FFMA (mode 0) or packed FFMA2 (mode 1) kernel. */
+double g6x_fp32_peak(int mode);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* G6_B200_H */
