@@ -287,12 +287,25 @@ void launch_force(int nj, int ni, const float4 *iA, const float4 *iB, const floa
     int n_iblocks = (ni + vi.ib - 1) / vi.ib;
     int ntiles = (nj + TILE - 1) / TILE;
     if (ntiles < 1) ntiles = 1;
-    // j-splits: fill the machine (resident CTAs x ~2 waves when there is work), >= 2 tiles per split
-    int target = G.sm_count * vi.ctas_per_sm;
-    int nsplit = (target + n_iblocks - 1) / n_iblocks;
-    if ((long long)n_iblocks * nsplit < 2LL * target && ntiles / std::max(nsplit, 1) >= 16) nsplit *= 2;
-    nsplit = std::min(nsplit, std::max(1, ntiles / 2));
-    nsplit = std::max(nsplit, 1);
+    // j-splits: pick the split count that minimises (waves x tiles per CTA), i.e. fills whole
+    // waves of resident CTAs; c0 ~ fixed per-CTA cost (prologue + reduction) in tile units.
+    const int slots = G.sm_count * vi.ctas_per_sm;
+    const double c0 = 1.5;
+    int best_ns = 1;
+    double best_cost = 1e300;
+    int max_ns = std::min(ntiles, std::max(1, 4 * slots / n_iblocks));
+    for (int ns = 1; ns <= max_ns; ns++) {
+        int tps_ = (ntiles + ns - 1) / ns;
+        int ns_ = (ntiles + tps_ - 1) / tps_;
+        long long ctas = (long long)ns_ * n_iblocks;
+        long long waves = (ctas + slots - 1) / slots;
+        double cost = (double)waves * (tps_ + c0);
+        if (cost < best_cost * 0.999) {
+            best_cost = cost;
+            best_ns = ns_;
+        }
+    }
+    int nsplit = best_ns;
     int tps = (ntiles + nsplit - 1) / nsplit;
     nsplit = (ntiles + tps - 1) / tps;
 

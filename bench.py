@@ -248,9 +248,10 @@ def run_b200(a):
             dist.barrier()
         torch.cuda.synchronize()
 
+    tstep = 2.0 ** -20            # a new time every step, so the predictor really runs each sweep
     for w in range(a.warmup):
         flush.fill_(w)
-        sweep(0.0)
+        sweep(tstep * (w + 1))
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -263,7 +264,7 @@ def run_b200(a):
     for k in range(a.steps):
         flush.fill_(k)            # evict j/i data from L2 between timed iterations
         ev[k][0].record()
-        sweep(0.0, record=True)
+        sweep(tstep * (a.warmup + k + 1), record=True)
         ev[k][1].record()
     barrier()
     t_wall1 = time.perf_counter()
@@ -301,19 +302,20 @@ def run_b200(a):
             g.calc(ids[:npipes], pos[:npipes], vel[:npipes], a.eps2)      # warm the ABI path
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            for _ in range(e2e_steps):
-                g.set_ti(0.0)
+            for k in range(e2e_steps):
+                g.set_ti(tstep * (100 + k))
                 out = g.calc(ids, pos, vel, a.eps2)
             torch.cuda.synchronize()
             dt = (time.perf_counter() - t0) / e2e_steps
             h2d, d2h = 48 * n, 60 * n
             how = "g6 C ABI, host double arrays, %d-particle chunks" % npipes
         else:
-            def e2e_step():
+            def e2e_step(k=[100]):
+                k[0] += 1
                 d_id.copy_(h_id, non_blocking=True)
                 d_x.copy_(h_x, non_blocking=True)
                 d_v.copy_(h_v, non_blocking=True)
-                sweep(0.0)
+                sweep(tstep * k[0])
                 h_sum.copy_(d_sum, non_blocking=True)
                 h_nn.copy_(d_nn, non_blocking=True)
             e2e_step()
