@@ -62,6 +62,8 @@ struct Context {
     int npipes = 16384;
     int ngb_cap = 1024;
     int variant = V_AUTO;
+    int refine = 1;        // Newton-refined rsqrt (accuracy first); 0 = raw MUFU.RSQ
+    bool ext_stream = false;
     int j_offset = 0;
     long long launches = 0;
 
@@ -235,13 +237,13 @@ void ensure_partials(size_t records)
     G.part_records = records;
 }
 
-template <int IPT, int NI_SLOTS, bool PACKED, int MINB>
-void launch_variant(const ForceArgs &a, dim3 grid, bool nn, bool list, cudaStream_t st)
+template <int IPT, int NI_SLOTS, bool PACKED, bool NR, int MINB>
+void launch_variant_nr(const ForceArgs &a, dim3 grid, bool nn, bool list, cudaStream_t st)
 {
     size_t smem = sizeof(ForceSmem);
 #define G6_LAUNCH(NN_, LIST_)                                                                       \
     do {                                                                                            \
-        auto kern = force_kernel<IPT, NI_SLOTS, NN_, LIST_, PACKED, MINB>;                          \
+        auto kern = force_kernel<IPT, NI_SLOTS, NN_, LIST_, PACKED, NR, MINB>;                      \
         static bool attr_set = false;                                                               \
         if (!attr_set) {                                                                            \
             CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
@@ -257,6 +259,15 @@ void launch_variant(const ForceArgs &a, dim3 grid, bool nn, bool list, cudaStrea
         G6_LAUNCH(false, false);
 #undef G6_LAUNCH
     CK(cudaGetLastError());
+}
+
+template <int IPT, int NI_SLOTS, bool PACKED, int MINB>
+void launch_variant(const ForceArgs &a, dim3 grid, bool nn, bool list, cudaStream_t st)
+{
+    if (G.refine)
+        launch_variant_nr<IPT, NI_SLOTS, PACKED, true, MINB>(a, grid, nn, list, st);
+    else
+        launch_variant_nr<IPT, NI_SLOTS, PACKED, false, MINB>(a, grid, nn, list, st);
 }
 
 const VariantInfo &variant_info(int v)
@@ -432,6 +443,7 @@ int g6_open_(int *id)
     G.npipes = std::max(1, env_int("G6_B200_NPIPES", 16384));
     G.ngb_cap = std::max(1, env_int("G6_B200_NGB_CAP", 1024));
     G.variant = env_int("G6_B200_VARIANT", V_AUTO);
+    G.refine = env_int("G6_B200_REFINE", 1);
     host_alloc(G.h_i, (size_t)3 * G.npipes);
     dev_alloc(G.d_i, (size_t)3 * G.npipes);
     dev_alloc(G.d_i2, (size_t)3 * G.npipes);
@@ -684,11 +696,19 @@ void force_j_particle_send(void)
 // ===========================================================================
 int g6x_version(void) { return 100; }
 
-int g6x_set_stream(void *cuda_stream)
+int g6x_set_stream(void *cuda_stream, int external)
 {
     require_open("g6x_set_stream");
     CK(cudaStreamSynchronize(G.stream));
-    G.stream = cuda_stream ? (cudaStream_t)cuda_stream : G.own_stream;
+    // a NULL handle with external != 0 is the legacy default stream (torch's default stream)
+    G.stream = external ? (cudaStream_t)cuda_stream : G.own_stream;
+    G.ext_stream = external != 0;
+    return 0;
+}
+
+int g6x_set_refine(int on)
+{
+    G.refine = on ? 1 : 0;
     return 0;
 }
 

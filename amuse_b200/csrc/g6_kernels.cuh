@@ -148,6 +148,14 @@ __device__ __forceinline__ float rsqrt_approx(float x)
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// One Newton-Raphson step on MUFU.RSQ (max rel. error 2^-22.9 -> ~1 ulp):
+//   e = 1 - x*y0^2 ; y = y0 + (y0/2)*e        (+4 FP32 ops per pair, see DESIGN.md "accuracy")
+__device__ __forceinline__ float rsqrt_refined(float x)
+{
+    float y0 = rsqrt_approx(x);
+    float e = fmaf(-x, y0 * y0, 1.0f);
+    return fmaf(0.5f * y0, e, y0);
+}
 typedef unsigned long long u64;
 __device__ __forceinline__ u64 pk(float lo, float hi)
 {
@@ -208,7 +216,7 @@ struct Acc7 {
 // 9 FADD (DS dx) + 3 FADD (dv) + 6 FMUL/FFMA (r2, xv) + 1 FADD (eps2) + MUFU.RSQ
 // + 5 FMUL + 9 FFMA + 1 FADD, plus guards.  Counted as 60 flop by convention
 // (src/amuse_ph4/src/jdata.cc:1038).
-template <bool NN, bool LIST>
+template <bool NN, bool LIST, bool NR>
 __device__ __forceinline__ void interact(const float4 a, const float4 b, const float4 c, int jaddr, float xh,
                                          float yh, float zh, float xl, float yl, float zl, float vx, float vy,
                                          float vz, int iid, float h2, float eps2, Acc7 &s, float &r2min,
@@ -221,7 +229,8 @@ __device__ __forceinline__ void interact(const float4 a, const float4 b, const f
     float r2 = dx * dx + dy * dy + dz * dz;
     float xv = dx * dvx + dy * dvy + dz * dvz;
     bool ok = (__float_as_int(b.w) != iid) && (r2 > TINYF);
-    float rinv = ok ? rsqrt_approx(r2 + eps2) : 0.f;
+    float rinv = NR ? rsqrt_refined(r2 + eps2) : rsqrt_approx(r2 + eps2);
+    rinv = ok ? rinv : 0.f;
     float rinv2 = rinv * rinv;
     float mrinv = a.w * rinv;
     float mr3 = mrinv * rinv2;
@@ -260,7 +269,7 @@ struct Acc7P {
     u64 ax, ay, az, jx, jy, jz, pot;
 };
 
-template <bool NN, bool LIST>
+template <bool NN, bool LIST, bool NR>
 __device__ __forceinline__ void interact2(const float4 a, const float4 b, const float4 c, int jaddr, const IPair &I,
                                           u64 eps2p, Acc7P &s, float &r2min0, int &jmin0, float &r2min1,
                                           int &jmin1, int i_global0, const ForceArgs &p)
@@ -280,9 +289,15 @@ __device__ __forceinline__ void interact2(const float4 a, const float4 b, const 
     int jid = __float_as_int(b.w);
     bool ok0 = (jid != I.id0) && (r20 > TINYF);
     bool ok1 = (jid != I.id1) && (r21 > TINYF);
-    float ri0 = ok0 ? rsqrt_approx(e0) : 0.f;
-    float ri1 = ok1 ? rsqrt_approx(e1) : 0.f;
+    float ri0 = rsqrt_approx(e0);
+    float ri1 = rsqrt_approx(e1);
     u64 rinv = pk(ri0, ri1);
+    if (NR) {  // packed Newton step: e = 1 - r2e*y0^2 ; y = y0 + (y0/2)*e
+        u64 e = fma2(mul2(r2e, pk(-1.f, -1.f)), mul2(rinv, rinv), pk(1.f, 1.f));
+        rinv = fma2(mul2(rinv, pk(0.5f, 0.5f)), e, rinv);
+        upk(rinv, ri0, ri1);
+    }
+    rinv = pk(ok0 ? ri0 : 0.f, ok1 ? ri1 : 0.f);
     u64 rinv2 = mul2(rinv, rinv);
     u64 mrinv = mul2(pk(a.w, a.w), rinv);
     u64 mr3 = mul2(mrinv, rinv2);
@@ -339,7 +354,7 @@ __device__ __forceinline__ u64 make_key(float r2min, int jmin_global)
 // partial sums are flushed to FP64 so that long sums keep ~1e-7 accuracy.
 // Partials of the j-slots are reduced with warp shuffles + shared memory, and the
 // partials of the j-splits by the last CTA to arrive (ticket), in fixed order.
-template <int IPT, int NI_SLOTS, bool NN, bool LIST, bool PACKED, int MINB>
+template <int IPT, int NI_SLOTS, bool NN, bool LIST, bool PACKED, bool NR, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) force_kernel(const ForceArgs p)
 {
     constexpr int NJ_SLOTS = THREADS / NI_SLOTS;
@@ -457,7 +472,7 @@ __global__ void __launch_bounds__(THREADS, MINB) force_kernel(const ForceArgs p)
                 const int jaddr = jtile + jj;
 #pragma unroll
                 for (int k = 0; k < IPT; k++)
-                    interact<NN, LIST>(a, b, c, jaddr, xh[k], yh[k], zh[k], xl[k], yl[k], zl[k], vx[k], vy[k], vz[k],
+                    interact<NN, LIST, NR>(a, b, c, jaddr, xh[k], yh[k], zh[k], xl[k], yl[k], zl[k], vx[k], vy[k], vz[k],
                                        iid[k], h2[k], eps2, S[k], r2min[k], jmin[k], i_of(k), p);
             }
 #pragma unroll
@@ -476,7 +491,7 @@ __global__ void __launch_bounds__(THREADS, MINB) force_kernel(const ForceArgs p)
                 const int jaddr = jtile + jj;
 #pragma unroll
                 for (int q = 0; q < NP; q++)
-                    interact2<NN, LIST>(a, b, c, jaddr, IP[q], eps2p, S[q], r2min[2 * q], jmin[2 * q],
+                    interact2<NN, LIST, NR>(a, b, c, jaddr, IP[q], eps2p, S[q], r2min[2 * q], jmin[2 * q],
                                         r2min[2 * q + 1], jmin[2 * q + 1], i_of(2 * q), p);
             }
 #pragma unroll

@@ -26,7 +26,7 @@ G6_SYMBOLS = [
     "g6_flush_jp_buffer", "g6_reset", "g6_reset_fofpga", "g6_reinitialize", "g6_get_number_of_pipelines",
     "g6_read_neighbour_list", "g6_get_neighbour_list", "g6_set_neighbour_list_sort_mode",
     "g6_get_neighbour_list_sort_mode", "g6_set_overflow_flag_test_mode", "force_j_particle_send",
-    "g6x_version", "g6x_set_stream", "g6x_set_j_offset", "g6x_set_j_particles", "g6x_predict",
+    "g6x_version", "g6x_set_stream", "g6x_set_refine", "g6x_set_j_offset", "g6x_set_j_particles", "g6x_predict",
     "g6x_calc_device", "g6x_resolve_nn", "g6x_synchronize", "g6x_launch_count", "g6x_get_predicted",
     "g6x_read_predicted", "g6x_time_predictor", "g6x_set_variant", "g6x_fp32_peak",
 ]
@@ -59,7 +59,8 @@ def load():
     L.g6calc_lasthalf2_.argtypes = [_pi, _pi, _pi, _ip, _dp, _dp, _pd, _dp, _dp, _dp, _dp, _ip]
     L.g6_read_neighbour_list_.argtypes = [_pi]
     L.g6_get_neighbour_list_.argtypes = [_pi, _pi, _pi, _pi, _ip]
-    L.g6x_set_stream.argtypes = [C.c_void_p]
+    L.g6x_set_stream.argtypes = [C.c_void_p, C.c_int]
+    L.g6x_set_refine.argtypes = [C.c_int]
     L.g6x_set_j_offset.argtypes = [C.c_int]
     L.g6x_set_j_particles.argtypes = [C.c_int, C.c_void_p, C.c_int, _ip, C.c_void_p, _dp, C.c_void_p,
                                       C.c_void_p, _dp, _dp]

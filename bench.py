@@ -201,7 +201,7 @@ def run_b200(a):
     j0, j1 = rank * per, min(n, (rank + 1) * per)
     g = g6lib.G6(local)
     L = g.L
-    L.g6x_set_stream(C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+    L.g6x_set_stream(C.c_void_p(torch.cuda.current_stream(dev).cuda_stream), 1)
     L.g6x_set_j_offset(j0)
     if a.variant:
         g.set_variant(a.variant)
@@ -297,7 +297,7 @@ def run_b200(a):
     if not a.no_e2e:
         e2e_steps = max(1, min(a.steps, 2))
         if world == 1:
-            L.g6x_set_stream(None)
+            L.g6x_set_stream(None, 0)
             g.set_ti(0.0)
             g.calc(ids[:npipes], pos[:npipes], vel[:npipes], a.eps2)      # warm the ABI path
             torch.cuda.synchronize()

@@ -133,9 +133,13 @@ void force_j_particle_send(void);
 
 /* Library/ABI version (major*100 + minor). */
 int g6x_version(void);
-/* Use an externally owned CUDA stream (a cudaStream_t passed as void*) for all
- * work; NULL restores the library's own stream. */
-int g6x_set_stream(void *cuda_stream);
+/* external != 0: run all work on the caller's CUDA stream (a cudaStream_t passed
+ * as void*; NULL is the legacy default stream).  external == 0: back to the
+ * library's own stream. */
+int g6x_set_stream(void *cuda_stream, int external);
+/* 1 (default): one Newton step on the reciprocal square root (per-pair error at
+ * the FP32 rounding floor); 0: raw MUFU.RSQ (2^-22.9), ~10 % faster. */
+int g6x_set_refine(int on);
 /* This process owns j-addresses whose GLOBAL address is local + offset (used
  * when j is sharded over ranks; the offset is packed in the nearest-neighbour
  * keys so a min-reduction over ranks is meaningful). */

@@ -40,6 +40,8 @@ def lib():
         L.oracle_predict.argtypes = [C.c_int, C.c_double, _dp, _dp, _dp, _dp, _dp, _dp, _dp]
         L.oracle_force.argtypes = [C.c_int, C.c_void_p, _dp, _dp, C.c_int, C.c_int, C.c_void_p,
                                    _dp, _dp, _dp, C.c_double, C.c_int, _dp, _dp, _dp, _ip, _dp]
+        L.oracle_force_scales.argtypes = [C.c_int, C.c_void_p, _dp, _dp, C.c_int, C.c_int, C.c_void_p,
+                                          _dp, _dp, _dp, C.c_double, C.c_int, _dp, _dp]
         L.oracle_combine.argtypes = [C.c_int, C.c_int, _dp, _dp, _dp, _ip, _dp, _dp, _dp, _dp, _ip, _dp]
         L.oracle_define_domain.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.oracle_neighbours.argtypes = [C.c_int, _dp, C.c_double, C.c_int, C.c_int, _ip, _dp, _dp, C.c_int, _ip]
@@ -61,7 +63,7 @@ def predict(t, time, pos, vel, acc, jerk):
     return pp, pv
 
 
-def force(ipos, ivel, mass, pred_pos, pred_vel, eps2, iid=None, jid=None, j_start=0, j_end=None):
+def force(ipos, ivel, mass, pred_pos, pred_vel, eps2, iid=None, jid=None, j_start=0, j_end=None, scales=False):
     """idata::get_partial_acc_and_jerk restatement.
 
     Returns dict(acc, jerk, pot, nn (j index), dnn)."""
@@ -82,6 +84,13 @@ def force(ipos, ivel, mass, pred_pos, pred_vel, eps2, iid=None, jid=None, j_star
     lib().oracle_force(ni, iid_.ctypes.data if use_ids else None, ipos, ivel, j_start, j_end,
                        jid_.ctypes.data if use_ids else None, _c(mass), _c(pred_pos), _c(pred_vel),
                        float(eps2), use_ids, acc, jerk, pot, nn, dnn)
+    sacc = np.empty(ni)
+    sjerk = np.empty(ni)
+    if scales:
+        lib().oracle_force_scales(ni, iid_.ctypes.data if use_ids else None, ipos, ivel, j_start, j_end,
+                                  jid_.ctypes.data if use_ids else None, _c(mass), _c(pred_pos), _c(pred_vel),
+                                  float(eps2), use_ids, sacc, sjerk)
+        return dict(acc=acc, jerk=jerk, pot=pot, nn=nn, dnn=dnn, sacc=sacc, sjerk=sjerk)
     return dict(acc=acc, jerk=jerk, pot=pot, nn=nn, dnn=dnn)
 
 

@@ -114,6 +114,46 @@ void oracle_force(int ni, const int *iid, const double *ipos, const double *ivel
 }
 
 /*
+ * Condition scales of the sums above (test metric only, no reference counterpart):
+ * sacc[i] = sum_j |acc_ij|, sjerk[i] = sum_j |jerk_ij| over the same pairs and
+ * with the same arithmetic as oracle_force.  A summation carried out in FP32
+ * pair arithmetic is backward stable iff its error is a small multiple of
+ * 2^-24 times these scales.
+ */
+void oracle_force_scales(int ni, const int *iid, const double *ipos, const double *ivel,
+                         int j_start, int j_end, const int *jid, const double *mass,
+                         const double *pred_pos, const double *pred_vel, double eps2,
+                         int use_ids, double *sacc, double *sjerk)
+{
+    for (int i = 0; i < ni; i++) {
+        double sa = 0, sj = 0;
+        for (int j = j_start; j < j_end; j++) {
+            if (!(mass[j] > ORACLE_TINY)) continue;
+            if (use_ids && iid && jid && iid[i] == jid[j]) continue;
+            double dx[3], dv[3], r2 = 0, xv = 0;
+            for (int k = 0; k < 3; k++) {
+                dx[k] = pred_pos[3 * j + k] - ipos[3 * i + k];
+                dv[k] = pred_vel[3 * j + k] - ivel[3 * i + k];
+                r2 += dx[k] * dx[k];
+                xv += dx[k] * dv[k];
+            }
+            double r2i = 1 / (r2 + eps2 + ORACLE_TINY);
+            double mr3i = mass[j] * sqrt(r2i) * r2i;
+            double a3 = -3 * xv * r2i, a2 = 0, j2 = 0;
+            for (int k = 0; k < 3; k++) {
+                double a = mr3i * dx[k], jk = mr3i * (dv[k] + a3 * dx[k]);
+                a2 += a * a;
+                j2 += jk * jk;
+            }
+            sa += sqrt(a2);
+            sj += sqrt(j2);
+        }
+        sacc[i] = sa;
+        sjerk[i] = sj;
+    }
+}
+
+/*
  * Combination of per-domain partial results, follows the reduction tail of
  * idata::get_acc_and_jerk(), src/amuse_ph4/src/idata.cc:284-313: sum pot, acc,
  * jerk; min over dnn; nn taken from the domain holding the minimum (first

@@ -63,6 +63,7 @@ static void load(jdata &jd, int n, const int *id, const double *mass,
 #ifdef GPU
     jd.have_gpu = true;
     jd.use_gpu = use_gpu;
+    jd.gpu_id = 0;          // jdata() leaves it uninitialised (jdata.h:89,137-170)
 #else
     jd.have_gpu = false;
     jd.use_gpu = false;

@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 
 from amuse_b200 import plummer as P
-from helpers import TOL, check_forces, check_nn, rel_err, rel_vec_err
+from helpers import TOL, check_forces, check_nn, error_report, rel_err, rel_vec_err
 
 pytestmark = pytest.mark.gpu
 
@@ -43,11 +43,28 @@ def test_golden_full_sweep_all_variants(g6, golden_dir, name, variant):
     g6.set_variant(variant)
     out = g6.calc(g["ids"], g["pos"], g["vel"], float(g["eps2"]))
     g6.set_variant(0)
+    print("%s variant %d: %s" % (name, variant, error_report(out, g)))
     check_forces(out, g, what="%s v%d" % (name, variant))
     check_nn(out["nn"], g["nn"], g["ids"], g["pos"], g["pos"])
     out2 = g6.calc(g["ids"], g["pos"], g["vel"], float(g["eps2"]), want_nn=False)   # lasthalf path
     for k in ("acc", "jerk", "pot"):
         assert np.array_equal(out[k], out2[k]), k
+
+
+def test_refine_switch(g6, golden_dir):
+    """g6x_set_refine(0) uses the raw MUFU.RSQ: same answers to ~1e-6, larger error than the default."""
+    g = _load(golden_dir, "ph4_plummer1k_eps1e-4.npz")
+    _fresh(g6, g["ids"], g["mass"], g["pos"], g["vel"])
+    a = g6.calc(g["ids"], g["pos"], g["vel"], 1e-4)
+    g6.L.g6x_set_refine(0)
+    try:
+        b = g6.calc(g["ids"], g["pos"], g["vel"], 1e-4)
+    finally:
+        g6.L.g6x_set_refine(1)
+    print("refined : %s" % error_report(a, g))
+    print("raw rsq : %s" % error_report(b, g))
+    assert rel_vec_err(a["acc"], g["acc"]).max() < rel_vec_err(b["acc"], g["acc"]).max()
+    assert rel_vec_err(b["acc"], g["acc"]).max() < 3e-6
 
 
 def test_golden_predictor_and_block_step_forces(g6, golden_dir):
@@ -182,10 +199,11 @@ def test_config1_n16k_through_abi_vs_cpu_forces(g6):
     _fresh(g6, ids, m, x, v)
     for eps2 in (0.0, 1e-4):
         out = g6.calc(ids, x, v, eps2)
-        ref = O.force(x, v, m, x, v, eps2)
-        ea, ej, ep = check_forces(out, ref, what="16k eps2=%g" % eps2)
+        ref = O.force(x, v, m, x, v, eps2, scales=True)
+        print("N=16k eps2=%g: %s" % (eps2, error_report(out, ref)))
+        check_forces(out, ref, what="16k eps2=%g" % eps2)
         nties = check_nn(out["nn"], ref["nn"], ids, x, x)
-        print("N=16k eps2=%g: max rel err acc %.2e jerk %.2e pot %.2e; nn tie mismatches %d" % (eps2, ea, ej, ep, nties))
+        print("N=16k eps2=%g: nn tie mismatches %d of %d" % (eps2, nties, n))
 
 
 def test_binaries_n8k(g6):
@@ -195,10 +213,10 @@ def test_binaries_n8k(g6):
     ids, m, x, v = P.add_binaries(m, x, v, fraction=0.1)
     _fresh(g6, ids, m, x, v)
     out = g6.calc(ids, x, v, 0.0)
-    ref = O.force(x, v, m, x, v, 0.0)
-    ea, ej, ep = check_forces(out, ref, what="binaries")
+    ref = O.force(x, v, m, x, v, 0.0, scales=True)
+    print("binaries N=8.8k: %s" % error_report(out, ref))
+    check_forces(out, ref, what="binaries")
     check_nn(out["nn"], ref["nn"], ids, x, x)
-    print("binaries N=8.8k: max rel err acc %.2e jerk %.2e pot %.2e" % (ea, ej, ep))
 
 
 def test_close_open_cycle(g6):
@@ -227,9 +245,10 @@ def test_full_size_n1m_sampled_oracle_and_properties(g6):
     _fresh(g6, ids, m, x, v)
     out = g6.calc(ids, x, v, 0.0)
     rnd = np.random.RandomState(0)
-    samp = np.sort(rnd.choice(n, 192, replace=False))
-    ref = O.force(x[samp], v[samp], m, x, v, 0.0, iid=ids[samp], jid=ids)
+    samp = np.sort(rnd.choice(n, 256, replace=False))
+    ref = O.force(x[samp], v[samp], m, x, v, 0.0, iid=ids[samp], jid=ids, scales=True)
     got = {k: out[k][samp] for k in out}
+    print("N=1M sample of 256: %s" % error_report(got, ref))
     ea, ej, ep = check_forces(got, ref, what="N=1M sample")
     check_nn(got["nn"], ref["nn"], ids, x[samp], x)
     fa = np.abs((m[:, None] * out["acc"]).sum(axis=0)).max() / (m * np.linalg.norm(out["acc"], axis=1)).sum()
@@ -253,7 +272,7 @@ def test_device_resident_entry_point_matches_abi(g6):
     out = g6.calc(ids, x, v, 1e-4)
     dev = torch.device("cuda:0")
     L = g6.L
-    L.g6x_set_stream(C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+    L.g6x_set_stream(C.c_void_p(torch.cuda.current_stream(dev).cuda_stream), 1)
     try:
         d_id = torch.from_numpy(ids).to(dev)
         d_x = torch.from_numpy(x).to(dev)
@@ -272,7 +291,7 @@ def test_device_resident_entry_point_matches_abi(g6):
         addr = (key & np.uint64(0xffffffff)).astype(np.int64)
         assert np.array_equal(ids[addr], out["nn"])
     finally:
-        L.g6x_set_stream(None)
+        L.g6x_set_stream(None, 0)
 
 
 def test_j_shards_combine_like_ph4_domains(g6):
