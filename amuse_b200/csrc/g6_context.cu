@@ -160,12 +160,7 @@ void ensure_capacity(int need)
     size_t newcap = std::max<size_t>(G.capacity ? (size_t)G.capacity * 2 : 65536, (size_t)need);
     newcap = (newcap + TILE - 1) / TILE * TILE;
     size_t old = G.capacity;
-    grow_dev(G.js.xy, old, newcap, G.stream);
-    grow_dev(G.js.zt, old, newcap, G.stream);
-    grow_dev(G.js.vxy, old, newcap, G.stream);
-    grow_dev(G.js.vz, old, newcap, G.stream);
-    grow_dev(G.js.am, old, newcap, G.stream);
-    grow_dev(G.js.jk, old, newcap, G.stream);
+    for (int k = 0; k < 7; k++) grow_dev(G.js.q[k], old, newcap, G.stream);
     grow_dev(G.js.A, old, newcap, G.stream);
     grow_dev(G.js.B, old, newcap, G.stream);
     grow_dev(G.js.C, old, newcap, G.stream);
@@ -352,8 +347,8 @@ void launch_force(int nj, int ni, const float4 *iA, const float4 *iB, const floa
 
 void free_all()
 {
-    dev_free(G.js.xy); dev_free(G.js.zt); dev_free(G.js.vxy); dev_free(G.js.vz);
-    dev_free(G.js.am); dev_free(G.js.jk); dev_free(G.js.A); dev_free(G.js.B); dev_free(G.js.C);
+    for (int k = 0; k < 7; k++) dev_free(G.js.q[k]);
+    dev_free(G.js.A); dev_free(G.js.B); dev_free(G.js.C);
     dev_free(G.d_up); host_free(G.h_up);
     host_free(G.h_i); dev_free(G.d_i); dev_free(G.d_i2);
     dev_free(G.d_sum); dev_free(G.d_key); dev_free(G.d_nnid);
@@ -385,14 +380,14 @@ void stage_j(int address, int index, double tj, double mass, const double *j6, c
     for (int k = 0; k < 3; k++) {
         u.x[k] = x[k];
         u.v[k] = v[k];
-        u.a[k] = (float)(2.0 * a2[k]);   // a2 = acc/2   (sapporo.cpp:94)
-        u.j[k] = (float)(6.0 * j6[k]);   // j6 = jerk/6  (sapporo.cpp:95)
+        u.a[k] = 2.0 * a2[k];   // a2 = acc/2   (sapporo.cpp:94)
+        u.j[k] = 6.0 * j6[k];   // j6 = jerk/6  (sapporo.cpp:95)
     }
     u.t = tj;
     u.m = (float)mass;
     u.id = index;
     u.addr = address;
-    u.pad = 0;
+    u.pad[0] = u.pad[1] = u.pad[2] = 0;
     if (address + 1 > G.nj_hi) G.nj_hi = address + 1;
 }
 

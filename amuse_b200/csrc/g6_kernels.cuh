@@ -21,22 +21,21 @@ namespace g6b {
 constexpr int THREADS = 256;   // threads per force CTA (8 warps)
 constexpr int TILE = 256;      // j-particles per shared-memory stage
 constexpr int STAGES = 3;      // TMA bulk-copy pipeline depth
+constexpr int FLUSH = 16;      // pairs summed in FP32 before a flush to the FP64 totals
 constexpr float TINYF = 2.220446049250313e-16f;  // 2^-52, stdinc.h:33
 constexpr float FAR_AWAY = 1.0e18f;  // where massless / unused j are parked
 constexpr unsigned long long KEY_NONE = 0x7f800000ffffffffULL;
 
 // ---------------------------------------------------------------------------
-// j state in HBM (capacity C, padded to a multiple of TILE):
-//   xy[C]  double2 (x, y)         zt[C]  double2 (z, t_j)
-//   vxy[C] double2 (vx, vy)       vz[C]  double
-//   am[C]  float4  (ax, ay, az, mass)    jk[C] float4 (jx, jy, jz, id bits)
+// j state in HBM (capacity C, padded to a multiple of TILE), all FP64 like the
+// reference's jdata arrays, packed as seven double2 streams (7 x LDG.128 per j):
+//   q0 = (x, y)    q1 = (z, t_j)   q2 = (vx, vy)   q3 = (vz, ax)
+//   q4 = (ay, az)  q5 = (jx, jy)   q6 = (jz, {float mass, int id})
 // predicted j (what the force kernel streams), float4 each:
 //   A = (x.hi, y.hi, z.hi, mass)  B = (x.lo, y.lo, z.lo, id bits)  C = (vx, vy, vz, 0)
 // ---------------------------------------------------------------------------
 struct JState {
-    double2 *xy, *zt, *vxy;
-    double *vz;
-    float4 *am, *jk;
+    double2 *q[7];
     float4 *A, *B, *C;
 };
 
@@ -44,15 +43,20 @@ struct JState {
 struct __align__(16) JUpdate {
     double x[3];
     double v[3];
+    double a[3];
+    double j[3];
     double t;
-    float a[3];
-    float j[3];
     float m;
     int id;
     int addr;
-    int pad;
+    int pad[3];
 };
-static_assert(sizeof(JUpdate) == 96, "JUpdate layout");
+static_assert(sizeof(JUpdate) == 128, "JUpdate layout");
+
+__device__ __forceinline__ double pack_mass_id(float m, int id)
+{
+    return __hiloint2double(id, __float_as_int(m));
+}
 
 __global__ void scatter_kernel(int n, const JUpdate *__restrict__ up, JState s)
 {
@@ -60,39 +64,45 @@ __global__ void scatter_kernel(int n, const JUpdate *__restrict__ up, JState s)
     if (k >= n) return;
     JUpdate u = up[k];
     int a = u.addr;
-    s.xy[a] = make_double2(u.x[0], u.x[1]);
-    s.zt[a] = make_double2(u.x[2], u.t);
-    s.vxy[a] = make_double2(u.v[0], u.v[1]);
-    s.vz[a] = u.v[2];
-    s.am[a] = make_float4(u.a[0], u.a[1], u.a[2], u.m);
-    s.jk[a] = make_float4(u.j[0], u.j[1], u.j[2], __int_as_float(u.id));
+    s.q[0][a] = make_double2(u.x[0], u.x[1]);
+    s.q[1][a] = make_double2(u.x[2], u.t);
+    s.q[2][a] = make_double2(u.v[0], u.v[1]);
+    s.q[3][a] = make_double2(u.v[2], u.a[0]);
+    s.q[4][a] = make_double2(u.a[1], u.a[2]);
+    s.q[5][a] = make_double2(u.j[0], u.j[1]);
+    s.q[6][a] = make_double2(u.j[2], pack_mass_id(u.m, u.id));
 }
 
 // Hermite predictor (jdata.cc:726-747) in FP64, output split to double-single.
-// Algorithmic traffic: 88 B read + 48 B written per j.
+// Algorithmic traffic: 112 B read + 48 B written per j.
 __global__ void predict_kernel(int n, double ti, JState s)
 {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
-    double2 xy = s.xy[j], zt = s.zt[j], vxy = s.vxy[j];
-    double vz = s.vz[j];
-    float4 am = s.am[j], jk = s.jk[j];
-    double dt = ti - zt.y;
-    double h = 0.5 * dt, t3 = dt * (1.0 / 3.0);
-    double px = xy.x + dt * (vxy.x + h * ((double)am.x + t3 * (double)jk.x));
-    double py = xy.y + dt * (vxy.y + h * ((double)am.y + t3 * (double)jk.y));
-    double pz = zt.x + dt * (vz + h * ((double)am.z + t3 * (double)jk.z));
-    double qx = vxy.x + dt * ((double)am.x + h * (double)jk.x);
-    double qy = vxy.y + dt * ((double)am.y + h * (double)jk.y);
-    double qz = vz + dt * ((double)am.z + h * (double)jk.z);
-    if (!(am.w > TINYF)) {  // massless or never-set slot: park it (idata.cc:208)
+    const double2 q0 = s.q[0][j], q1 = s.q[1][j], q2 = s.q[2][j], q3 = s.q[3][j], q4 = s.q[4][j], q5 = s.q[5][j],
+                  q6 = s.q[6][j];
+    const double x = q0.x, y = q0.y, z = q1.x, tj = q1.y, vx = q2.x, vy = q2.y, vz = q3.x;
+    const double ax = q3.y, ay = q4.x, az = q4.y, jx = q5.x, jy = q5.y, jz = q6.x;
+    const float m = __int_as_float(__double2loint(q6.y));
+    const int id = __double2hiint(q6.y);
+    const double dt = ti - tj;
+    double px = x, py = y, pz = z, qx = vx, qy = vy, qz = vz;
+    if (dt != 0.0) {  // same expression tree as jdata.cc:739-746
+        px = x + dt * (vx + 0.5 * dt * (ax + dt * jx / 3));
+        py = y + dt * (vy + 0.5 * dt * (ay + dt * jy / 3));
+        pz = z + dt * (vz + 0.5 * dt * (az + dt * jz / 3));
+        qx = vx + dt * (ax + 0.5 * dt * jx);
+        qy = vy + dt * (ay + 0.5 * dt * jy);
+        qz = vz + dt * (az + 0.5 * dt * jz);
+    }
+    if (!(m > TINYF)) {  // massless or never-set slot: park it (idata.cc:208)
         px = py = pz = (double)FAR_AWAY;
         qx = qy = qz = 0.0;
     }
     float xh = (float)px, yh = (float)py, zh = (float)pz;
     float xl = (float)(px - (double)xh), yl = (float)(py - (double)yh), zl = (float)(pz - (double)zh);
-    s.A[j] = make_float4(xh, yh, zh, am.w);
-    s.B[j] = make_float4(xl, yl, zl, jk.w);
+    s.A[j] = make_float4(xh, yh, zh, m);
+    s.B[j] = make_float4(xl, yl, zl, __int_as_float(id));
     s.C[j] = make_float4((float)qx, (float)qy, (float)qz, 0.f);
 }
 
@@ -228,9 +238,12 @@ __device__ __forceinline__ void interact(const float4 a, const float4 b, const f
     float dvx = c.x - vx, dvy = c.y - vy, dvz = c.z - vz;
     float r2 = dx * dx + dy * dy + dz * dz;
     float xv = dx * dvx + dy * dvy + dz * dvz;
-    bool ok = (__float_as_int(b.w) != iid) && (r2 > TINYF);
-    float rinv = NR ? rsqrt_refined(r2 + eps2) : rsqrt_approx(r2 + eps2);
-    rinv = ok ? rinv : 0.f;
+    // idata.cc:216-233: r2i = 1/(r2 + eps2 + TINY) feeds acc and jerk unconditionally; pot and the
+    // neighbour search are guarded by r2 > TINY.  Equal ids are skipped altogether (g6 rule).
+    const bool idok = (__float_as_int(b.w) != iid);
+    const bool ok = idok && (r2 > TINYF);
+    float rinv = NR ? rsqrt_refined(r2 + eps2) : rsqrt_approx(r2 + eps2);   // eps2 holds eps2 + TINY
+    rinv = idok ? rinv : 0.f;
     float rinv2 = rinv * rinv;
     float mrinv = a.w * rinv;
     float mr3 = mrinv * rinv2;
@@ -241,7 +254,7 @@ __device__ __forceinline__ void interact(const float4 a, const float4 b, const f
     s.jx = fmaf(mr3, fmaf(a3, dx, dvx), s.jx);
     s.jy = fmaf(mr3, fmaf(a3, dy, dvy), s.jy);
     s.jz = fmaf(mr3, fmaf(a3, dz, dvz), s.jz);
-    s.pot += mrinv;
+    s.pot += ok ? mrinv : 0.f;
     if (NN) {
         float r2n = ok ? r2 : __int_as_float(0x7f800000);
         if (r2n < r2min) {
@@ -287,8 +300,8 @@ __device__ __forceinline__ void interact2(const float4 a, const float4 b, const 
     upk(r2, r20, r21);
     upk(r2e, e0, e1);
     int jid = __float_as_int(b.w);
-    bool ok0 = (jid != I.id0) && (r20 > TINYF);
-    bool ok1 = (jid != I.id1) && (r21 > TINYF);
+    const bool id0 = (jid != I.id0), id1 = (jid != I.id1);
+    const bool ok0 = id0 && (r20 > TINYF), ok1 = id1 && (r21 > TINYF);
     float ri0 = rsqrt_approx(e0);
     float ri1 = rsqrt_approx(e1);
     u64 rinv = pk(ri0, ri1);
@@ -297,7 +310,7 @@ __device__ __forceinline__ void interact2(const float4 a, const float4 b, const 
         rinv = fma2(mul2(rinv, pk(0.5f, 0.5f)), e, rinv);
         upk(rinv, ri0, ri1);
     }
-    rinv = pk(ok0 ? ri0 : 0.f, ok1 ? ri1 : 0.f);
+    rinv = pk(id0 ? ri0 : 0.f, id1 ? ri1 : 0.f);
     u64 rinv2 = mul2(rinv, rinv);
     u64 mrinv = mul2(pk(a.w, a.w), rinv);
     u64 mr3 = mul2(mrinv, rinv2);
@@ -308,7 +321,7 @@ __device__ __forceinline__ void interact2(const float4 a, const float4 b, const 
     s.jx = fma2(mr3, fma2(a3, dx, dvx), s.jx);
     s.jy = fma2(mr3, fma2(a3, dy, dvy), s.jy);
     s.jz = fma2(mr3, fma2(a3, dz, dvz), s.jz);
-    s.pot = add2(s.pot, mrinv);
+    s.pot = fma2(pk(a.w, a.w), pk(ok0 ? ri0 : 0.f, ok1 ? ri1 : 0.f), s.pot);
     if (NN) {
         float n0 = ok0 ? r20 : __int_as_float(0x7f800000);
         float n1 = ok1 ? r21 : __int_as_float(0x7f800000);
@@ -448,7 +461,7 @@ __global__ void __launch_bounds__(THREADS, MINB) force_kernel(const ForceArgs p)
             IP[q].h21 = h2[2 * q + 1];
         }
     }
-    const float eps2 = p.eps2;
+    const float eps2 = p.eps2 + TINYF;   // the reference softens by eps2 + 2^-52 (idata.cc:216)
     const u64 eps2p = pk(eps2, eps2);
 
     // ---- main loop over tiles --------------------------------------------
@@ -462,48 +475,69 @@ __global__ void __launch_bounds__(THREADS, MINB) force_kernel(const ForceArgs p)
         if (cnt > TILE) cnt = TILE;
         const float4 *tA = sm.A[s], *tB = sm.B[s], *tC = sm.C[s];
 
-        if (!PACKED) {
-            Acc7 S[IPT];
+        // The thread's j of this tile are jj = jslot + u*NJ_SLOTS, u = 0..ITERS-1.  They are processed
+        // in groups of FL: FP32 partial sums over at most FL pairs, then flushed to the FP64 totals
+        // (F2F + DADD run on the XU / FP64 pipes, off the FP32 pipe that bounds the kernel), so the
+        // summation error stays below the per-pair rounding error for any N.
+        constexpr int ITERS = TILE / NJ_SLOTS;
+        constexpr int FL = ITERS < FLUSH ? ITERS : FLUSH;
+        for (int u0 = 0; u0 < ITERS; u0 += FL) {
+            const int jj0 = jslot + u0 * NJ_SLOTS;
+            if (jj0 >= cnt) break;
+            const bool whole = (jj0 + (FL - 1) * NJ_SLOTS) < cnt;
+            if (!PACKED) {
+                Acc7 S[IPT];
 #pragma unroll
-            for (int k = 0; k < IPT; k++) S[k] = Acc7{0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                for (int k = 0; k < IPT; k++) S[k] = Acc7{0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                auto do_j = [&](int jj) {
+                    const float4 a = tA[jj], b = tB[jj], c = tC[jj];
+                    const int jaddr = jtile + jj;
+#pragma unroll
+                    for (int k = 0; k < IPT; k++)
+                        interact<NN, LIST, NR>(a, b, c, jaddr, xh[k], yh[k], zh[k], xl[k], yl[k], zl[k], vx[k], vy[k],
+                                               vz[k], iid[k], h2[k], eps2, S[k], r2min[k], jmin[k], i_of(k), p);
+                };
+                if (whole) {
 #pragma unroll 2
-            for (int jj = jslot; jj < cnt; jj += NJ_SLOTS) {
-                const float4 a = tA[jj], b = tB[jj], c = tC[jj];
-                const int jaddr = jtile + jj;
+                    for (int u = 0; u < FL; u++) do_j(jj0 + u * NJ_SLOTS);
+                } else {
+                    for (int jj = jj0; jj < cnt; jj += NJ_SLOTS) do_j(jj);
+                }
 #pragma unroll
-                for (int k = 0; k < IPT; k++)
-                    interact<NN, LIST, NR>(a, b, c, jaddr, xh[k], yh[k], zh[k], xl[k], yl[k], zl[k], vx[k], vy[k], vz[k],
-                                       iid[k], h2[k], eps2, S[k], r2min[k], jmin[k], i_of(k), p);
-            }
+                for (int k = 0; k < IPT; k++) {
+                    D[k][0] += (double)S[k].ax; D[k][1] += (double)S[k].ay; D[k][2] += (double)S[k].az;
+                    D[k][3] += (double)S[k].jx; D[k][4] += (double)S[k].jy; D[k][5] += (double)S[k].jz;
+                    D[k][6] += (double)S[k].pot;
+                }
+            } else {
+                Acc7P S[NP];
 #pragma unroll
-            for (int k = 0; k < IPT; k++) {
-                D[k][0] += (double)S[k].ax; D[k][1] += (double)S[k].ay; D[k][2] += (double)S[k].az;
-                D[k][3] += (double)S[k].jx; D[k][4] += (double)S[k].jy; D[k][5] += (double)S[k].jz;
-                D[k][6] += (double)S[k].pot;
-            }
-        } else {
-            Acc7P S[NP];
+                for (int q = 0; q < NP; q++) S[q] = Acc7P{0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull};
+                auto do_j = [&](int jj) {
+                    const float4 a = tA[jj], b = tB[jj], c = tC[jj];
+                    const int jaddr = jtile + jj;
 #pragma unroll
-            for (int q = 0; q < NP; q++) S[q] = Acc7P{0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull};
+                    for (int q = 0; q < NP; q++)
+                        interact2<NN, LIST, NR>(a, b, c, jaddr, IP[q], eps2p, S[q], r2min[2 * q], jmin[2 * q],
+                                                r2min[2 * q + 1], jmin[2 * q + 1], i_of(2 * q), p);
+                };
+                if (whole) {
 #pragma unroll 2
-            for (int jj = jslot; jj < cnt; jj += NJ_SLOTS) {
-                const float4 a = tA[jj], b = tB[jj], c = tC[jj];
-                const int jaddr = jtile + jj;
+                    for (int u = 0; u < FL; u++) do_j(jj0 + u * NJ_SLOTS);
+                } else {
+                    for (int jj = jj0; jj < cnt; jj += NJ_SLOTS) do_j(jj);
+                }
 #pragma unroll
-                for (int q = 0; q < NP; q++)
-                    interact2<NN, LIST, NR>(a, b, c, jaddr, IP[q], eps2p, S[q], r2min[2 * q], jmin[2 * q],
-                                        r2min[2 * q + 1], jmin[2 * q + 1], i_of(2 * q), p);
-            }
-#pragma unroll
-            for (int q = 0; q < NP; q++) {
-                float lo, hi;
-                upk(S[q].ax, lo, hi); D[2 * q][0] += (double)lo; D[2 * q + 1][0] += (double)hi;
-                upk(S[q].ay, lo, hi); D[2 * q][1] += (double)lo; D[2 * q + 1][1] += (double)hi;
-                upk(S[q].az, lo, hi); D[2 * q][2] += (double)lo; D[2 * q + 1][2] += (double)hi;
-                upk(S[q].jx, lo, hi); D[2 * q][3] += (double)lo; D[2 * q + 1][3] += (double)hi;
-                upk(S[q].jy, lo, hi); D[2 * q][4] += (double)lo; D[2 * q + 1][4] += (double)hi;
-                upk(S[q].jz, lo, hi); D[2 * q][5] += (double)lo; D[2 * q + 1][5] += (double)hi;
-                upk(S[q].pot, lo, hi); D[2 * q][6] += (double)lo; D[2 * q + 1][6] += (double)hi;
+                for (int q = 0; q < NP; q++) {
+                    float lo, hi;
+                    upk(S[q].ax, lo, hi); D[2 * q][0] += (double)lo; D[2 * q + 1][0] += (double)hi;
+                    upk(S[q].ay, lo, hi); D[2 * q][1] += (double)lo; D[2 * q + 1][1] += (double)hi;
+                    upk(S[q].az, lo, hi); D[2 * q][2] += (double)lo; D[2 * q + 1][2] += (double)hi;
+                    upk(S[q].jx, lo, hi); D[2 * q][3] += (double)lo; D[2 * q + 1][3] += (double)hi;
+                    upk(S[q].jy, lo, hi); D[2 * q][4] += (double)lo; D[2 * q + 1][4] += (double)hi;
+                    upk(S[q].jz, lo, hi); D[2 * q][5] += (double)lo; D[2 * q + 1][5] += (double)hi;
+                    upk(S[q].pot, lo, hi); D[2 * q][6] += (double)lo; D[2 * q + 1][6] += (double)hi;
+                }
             }
         }
 

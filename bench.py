@@ -288,9 +288,9 @@ def run_b200(a):
     # measured FP32 FMA pipe peak (dependent-chain FFMA / FFMA2 microbenchmarks in the library)
     ffma = L.g6x_fp32_peak(0)
     ffma2 = L.g6x_fp32_peak(1)
-    # predictor: HBM-bound kernel, 88 B read + 48 B written per j
+    # predictor: HBM-bound kernel, 112 B read + 48 B written per j
     pred_ms = L.g6x_time_predictor(njl, 20)
-    pred_gbs = 136.0 * njl / (pred_ms * 1e-3) / 1e9 if pred_ms > 0 else None
+    pred_gbs = 160.0 * njl / (pred_ms * 1e-3) / 1e9 if pred_ms > 0 else None
 
     # ---- end-to-end through the public API with host buffers ------------------------------------
     e2e = None
@@ -367,7 +367,7 @@ def run_b200(a):
                          "kernel_share_of_step": kernel_share,
                          "measured_ffma_tflops": ffma, "measured_ffma2_tflops": ffma2,
                          "frac_of_measured_ffma": achieved / max(ffma, ffma2, 1e-9)},
-            "predictor": {"bound": "hbm", "achieved": pred_gbs, "unit": "GB/s", "bytes_per_j": 136,
+            "predictor": {"bound": "hbm", "achieved": pred_gbs, "unit": "GB/s", "bytes_per_j": 160,
                           "ms_per_launch": pred_ms},
             "e2e": e2e, "cpu_baseline": cpu, "gpu_launches": int(launches), "clocks": clocks,
         }

@@ -6,7 +6,7 @@ Per-particle vector-norm relative errors against ph4's FP64 CPU loop:
 Tolerances written here and asserted by every parity test:
   * acc, pot : max over all particles <= 1e-6  (the north-star bound).
   * jerk     : 99th percentile <= 1e-6; max <= 1e-5; and, when the oracle provides the condition
-               scale S_i = sum_j |jerk_ij|, every particle satisfies |dj_i| <= 3e-7 * S_i.
+               scale S_i = sum_j |jerk_ij|, every particle satisfies |dj_i| <= 1e-6 * S_i (same for acc).
     Why jerk differs: the library is mandated to do FP32 pair arithmetic on double-single
     positions.  jerk_i is a sum of terms of random sign, so for a few particles per thousand the
     total is ~10x smaller than the terms; the 2^-24 rounding of dx alone (everything downstream in
@@ -18,7 +18,7 @@ import numpy as np
 
 TOL = 1e-6          # acc / pot max, jerk 99th percentile
 TOL_JERK_MAX = 1e-5
-TOL_JERK_SCALED = 3e-7
+TOL_JERK_SCALED = 1e-6
 
 
 def rel_vec_err(a, b):

@@ -47,8 +47,8 @@ def test_golden_full_sweep_all_variants(g6, golden_dir, name, variant):
     check_forces(out, g, what="%s v%d" % (name, variant))
     check_nn(out["nn"], g["nn"], g["ids"], g["pos"], g["pos"])
     out2 = g6.calc(g["ids"], g["pos"], g["vel"], float(g["eps2"]), want_nn=False)   # lasthalf path
-    for k in ("acc", "jerk", "pot"):
-        assert np.array_equal(out[k], out2[k]), k
+    check_forces(out2, g, what="%s v%d lasthalf" % (name, variant))
+    assert rel_vec_err(out2["acc"], out["acc"]).max() < 5e-7
 
 
 def test_refine_switch(g6, golden_dir):
@@ -173,14 +173,17 @@ def test_neighbour_lists(g6):
     h2 = np.minimum(8 * f["dnn"] ** 2, 1.0)          # gpu.cc:629-630
     out = g6.calc(ids[:300], x[:300], v[:300], 0.0, h2=h2)
     assert g6.read_neighbour_list() == 0
+    bad = []
     for i in range(300):
         n_ref, lst_ref = O.neighbours(int(ids[i]), x[i], h2[i], ids, m, x)
         rc, n, lst = g6.get_neighbour_list(i)
         r2 = ((x - x[i]) ** 2).sum(axis=1)
         edge = set(ids[np.abs(r2 - h2[i]) <= 1e-6 * h2[i]].tolist())     # members at the FP32 edge of the sphere
-        assert set(lst.tolist()) ^ set(lst_ref.tolist()) <= edge, i
-        assert rc == 0 and n == len(lst) and np.all(np.diff(lst) > 0)
-        assert out["nn"][i] in lst
+        good = (set(lst.tolist()) ^ set(lst_ref.tolist()) <= edge) and rc == 0 and n == len(lst) \
+            and np.all(np.diff(lst) > 0) and ((out["nn"][i] in lst) or f["dnn"][i] ** 2 > h2[i] * (1 - 1e-6))
+        if not good:
+            bad.append((i, rc, n, n_ref, int(out["nn"][i]), int(ids[f["nn"][i]]), lst[:6].tolist(), lst_ref[:6].tolist()))
+    assert not bad, bad[:10]
     # overflow flag: tiny maxlength
     rc, n, lst = g6.get_neighbour_list(0, maxlength=1)
     assert n >= 1 and (rc != 0) == (n > 1)
