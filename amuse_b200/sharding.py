@@ -1,0 +1,52 @@
+"""j-domain decomposition over ranks and the cross-rank reduction of partial forces.
+
+Host-side mirror of the only data-parallel strategy the reference has on this path
+(SURVEY.md section 2.6): every rank holds the contiguous j-slice of
+``jdata::define_domain`` (``src/amuse_ph4/src/jdata.cc:56-67``), computes partial forces on the
+whole i-block against it, and the partials are combined like the tail of
+``idata::get_acc_and_jerk`` (``src/amuse_ph4/src/idata.cc:284-313``):
+
+    sum    of pot/acc/jerk               -> all_reduce(SUM) on the [ni, 7] double sums
+    min    of nearest-neighbour distance -> all_reduce(MIN) on 64-bit keys (float bits of r^2 << 32 | address)
+    argmin "only the owner is non-zero"  -> all_reduce(SUM) on the resolved ids
+
+The functions take torch tensors on any device and use whatever process group is active
+(NCCL over NVLink on the B200 box, gloo in the CPU tests).  No arithmetic of the force path
+lives here.
+"""
+KEY_NONE = 0x7F800000FFFFFFFF
+
+
+def define_domain(nj, size, rank):
+    """[j_start, j_end) of `rank` -- jdata::define_domain, jdata.cc:56-67."""
+    n = nj // size
+    if n * size < nj:
+        n += 1
+    j_start = rank * n
+    j_end = j_start + n
+    if rank == size - 1:
+        j_end = nj
+    if j_start >= nj:
+        j_end = j_start
+    return j_start, min(j_end, nj)
+
+
+def combine_partials(d_sum, d_key, resolve_ids, group=None):
+    """In-place cross-rank combination.
+
+    d_sum : [ni, 7] float64 partial (acc xyz, jerk xyz, sum m/r) of this rank's j-shard
+    d_key : [ni]    int64 nearest-neighbour keys of this rank's shard
+    resolve_ids(d_key_reduced) -> [ni] int32 tensor: id of the winner if this rank owns its
+        address, 0 otherwise, -1 on rank 0 where there is no neighbour at all
+        (``g6x_resolve_nn``).
+    Returns the [ni] int32 nearest-neighbour ids, identical on every rank.
+    """
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return resolve_ids(d_key)
+    dist.all_reduce(d_sum, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(d_key, op=dist.ReduceOp.MIN, group=group)
+    d_nn = resolve_ids(d_key)
+    dist.all_reduce(d_nn, op=dist.ReduceOp.SUM, group=group)
+    return d_nn

@@ -178,7 +178,7 @@ class ClockSampler:
 def run_b200(a):
     import torch
     import torch.distributed as dist
-    from amuse_b200 import g6lib, plummer as P
+    from amuse_b200 import g6lib, plummer as P, sharding as S
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -197,8 +197,7 @@ def run_b200(a):
     mass, pos, vel = P.new_plummer_model(n, seed=a.seed)      # identical on every rank
     ids = np.arange(1, n + 1, dtype=np.int32)
     # j-domain of this rank: jdata::define_domain (src/amuse_ph4/src/jdata.cc:56-67)
-    per = (n + world - 1) // world
-    j0, j1 = rank * per, min(n, (rank + 1) * per)
+    j0, j1 = S.define_domain(n, world, rank)
     g = g6lib.G6(local)
     L = g.L
     L.g6x_set_stream(C.c_void_p(torch.cuda.current_stream(dev).cuda_stream), 1)
@@ -223,6 +222,10 @@ def run_b200(a):
 
     chunk_events = []
 
+    def resolve(keys):
+        L.g6x_resolve_nn(n, keys.data_ptr(), rank, d_nn.data_ptr())
+        return d_nn
+
     def sweep(t, record=False):
         """predict + force sweep + cross-rank reduction; everything on the current stream."""
         L.g6x_predict(njl, float(t))
@@ -237,11 +240,8 @@ def run_b200(a):
             if record:
                 e1.record()
                 chunk_events.append((e0, e1, ni))
-        if world > 1:
-            dist.all_reduce(d_sum, op=dist.ReduceOp.SUM)
-            dist.all_reduce(d_key, op=dist.ReduceOp.MIN)
-            L.g6x_resolve_nn(n, d_key.data_ptr(), rank, d_nn.data_ptr())
-            dist.all_reduce(d_nn, op=dist.ReduceOp.SUM)
+        if world > 1:      # idata.cc:284-313 on the device: sum, min-key, owner-resolved id
+            S.combine_partials(d_sum, d_key, resolve)
 
     def barrier():
         if world > 1:
