@@ -852,10 +852,15 @@ double g6x_fp32_peak(int mode)
     float best = 1e30f;
     for (int r = 0; r < 6; r++) {
         CK(cudaEventRecord(e0, G.stream));
-        if (mode == 0)
-            fp32_peak_kernel<0><<<blocks, 256, 0, G.stream>>>(d, iters, 1.0f);
-        else
-            fp32_peak_kernel<1><<<blocks, 256, 0, G.stream>>>(d, iters, 1.0f);
+        switch (mode) {
+            case 0: fp32_peak_kernel<0><<<blocks, 256, 0, G.stream>>>(d, iters, 1.0f); break;
+            case 1: fp32_peak_kernel<1><<<blocks, 256, 0, G.stream>>>(d, iters, 1.0f); break;
+            case 2: fp32_peak_kernel<2><<<blocks, 256, 0, G.stream>>>(d, iters, 1.0f); break;
+            case 3: fp32_peak_kernel<3><<<blocks, 256, 0, G.stream>>>(d, iters, 1.0f); break;
+            case 4: fp32_peak_kernel<4><<<blocks, 256, 0, G.stream>>>(d, iters, 1.0f); break;
+            case 5: fp32_peak_kernel<5><<<blocks, 256, 0, G.stream>>>(d, iters, 1.0f); break;
+            default: fp32_peak_kernel<6><<<blocks, 256, 0, G.stream>>>(d, iters, 1.0f); break;
+        }
         CK(cudaEventRecord(e1, G.stream));
         CK(cudaEventSynchronize(e1));
         float ms;
@@ -866,7 +871,7 @@ double g6x_fp32_peak(int mode)
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     dev_free(d);
-    double fmas = (double)blocks * 256 * iters * 8 * 8 * (mode == 0 ? 1 : 2);
+    double fmas = (double)blocks * 256 * iters * 8 * 8 * ((mode == 0 || mode == 2) ? 1 : 2);
     return 2.0 * fmas / (best * 1e-3) / 1e12;
 }
 

@@ -21,7 +21,14 @@ namespace g6b {
 constexpr int THREADS = 256;   // threads per force CTA (8 warps)
 constexpr int TILE = 256;      // j-particles per shared-memory stage
 constexpr int STAGES = 3;      // TMA bulk-copy pipeline depth
-constexpr int FLUSH = 16;      // pairs summed in FP32 before a flush to the FP64 totals
+#ifndef G6_FLUSH
+#define G6_FLUSH 64
+#endif
+#ifndef G6_UNROLL
+#define G6_UNROLL 2
+#endif
+constexpr int UNROLL = G6_UNROLL;  // j-iterations unrolled in the hot loop
+constexpr int FLUSH = G6_FLUSH;  // pairs summed in FP32 before a flush to the FP64 totals
 constexpr float TINYF = 2.220446049250313e-16f;  // 2^-52, stdinc.h:33
 constexpr float FAR_AWAY = 1.0e18f;  // where massless / unused j are parked
 constexpr unsigned long long KEY_NONE = 0x7f800000ffffffffULL;
@@ -305,9 +312,9 @@ __device__ __forceinline__ void interact2(const float4 a, const float4 b, const 
     float ri0 = rsqrt_approx(e0);
     float ri1 = rsqrt_approx(e1);
     u64 rinv = pk(ri0, ri1);
-    if (NR) {  // packed Newton step: e = 1 - r2e*y0^2 ; y = y0 + (y0/2)*e
-        u64 e = fma2(mul2(r2e, pk(-1.f, -1.f)), mul2(rinv, rinv), pk(1.f, 1.f));
-        rinv = fma2(mul2(rinv, pk(0.5f, 0.5f)), e, rinv);
+    if (NR) {  // packed Newton step: e = r2e*y0^2 - 1 ; y = y0 - (y0/2)*e   (4 packed ops)
+        u64 e = fma2(r2e, mul2(rinv, rinv), pk(-1.f, -1.f));
+        rinv = fma2(mul2(rinv, pk(-0.5f, -0.5f)), e, rinv);
         upk(rinv, ri0, ri1);
     }
     rinv = pk(id0 ? ri0 : 0.f, id1 ? ri1 : 0.f);
@@ -498,7 +505,7 @@ __global__ void __launch_bounds__(THREADS, MINB) force_kernel(const ForceArgs p)
                                                vz[k], iid[k], h2[k], eps2, S[k], r2min[k], jmin[k], i_of(k), p);
                 };
                 if (whole) {
-#pragma unroll 2
+#pragma unroll UNROLL
                     for (int u = 0; u < FL; u++) do_j(jj0 + u * NJ_SLOTS);
                 } else {
                     for (int jj = jj0; jj < cnt; jj += NJ_SLOTS) do_j(jj);
@@ -522,7 +529,7 @@ __global__ void __launch_bounds__(THREADS, MINB) force_kernel(const ForceArgs p)
                                                 r2min[2 * q + 1], jmin[2 * q + 1], i_of(2 * q), p);
                 };
                 if (whole) {
-#pragma unroll 2
+#pragma unroll UNROLL
                     for (int u = 0; u < FL; u++) do_j(jj0 + u * NJ_SLOTS);
                 } else {
                     for (int jj = jj0; jj < cnt; jj += NJ_SLOTS) do_j(jj);
@@ -689,17 +696,25 @@ __global__ void resolve_nn_kernel(int ni, const u64 *__restrict__ key, int rank,
 template <int MODE>
 __global__ void __launch_bounds__(256) fp32_peak_kernel(float *out, int iters, float seed)
 {
+    // MODE 0: scalar FFMA, operands mostly from the reuse cache      (x = x*m + a)
+    // MODE 1: packed FFMA2, same pattern
+    // MODE 2: scalar FFMA, three distinct rotating register operands (x[c] = x[c+1]*x[c+2] + x[c])
+    // MODE 3: packed FFMA2, three distinct rotating 64-bit operands
+    // MODE 4: packed FFMA2 with a broadcast 32-bit operand           (x[c] = x[c+1]*s + x[c])
+    // MODE 5: MODE 3 with one ALU op (FMNMX) per two FFMA2, as in the force loop
+    // MODE 6: packed FADD2, two distinct operands
     constexpr int CH = 8;
-    if (MODE == 0) {
+    if (MODE == 0 || MODE == 2) {
         float x[CH];
 #pragma unroll
-        for (int c = 0; c < CH; c++) x[c] = seed + threadIdx.x * 1e-6f + c;
+        for (int c = 0; c < CH; c++) x[c] = seed + threadIdx.x * 1e-6f + c * 0.001f;
         float m = 0.999999f, a = 1e-7f + seed;
         for (int it = 0; it < iters; it++) {
 #pragma unroll
             for (int u = 0; u < 8; u++)
 #pragma unroll
-                for (int c = 0; c < CH; c++) x[c] = fmaf(x[c], m, a);
+                for (int c = 0; c < CH; c++)
+                    x[c] = (MODE == 0) ? fmaf(x[c], m, a) : fmaf(x[(c + 1) % CH], x[(c + 2) % CH], x[c]);
         }
         float s = 0;
 #pragma unroll
@@ -707,16 +722,28 @@ __global__ void __launch_bounds__(256) fp32_peak_kernel(float *out, int iters, f
         if (s == 12345.678f) out[threadIdx.x] = s;
     } else {
         u64 x[CH];
+        float mn = seed;
 #pragma unroll
-        for (int c = 0; c < CH; c++) x[c] = pk(seed + threadIdx.x * 1e-6f + c, seed + c + 0.5f);
+        for (int c = 0; c < CH; c++) x[c] = pk(seed + threadIdx.x * 1e-6f + c * 0.001f, seed + c * 0.002f + 0.5f);
         u64 m = pk(0.999999f, 0.999998f), a = pk(1e-7f + seed, 2e-7f + seed);
+        float sc = 0.99999f + seed * 1e-9f;
         for (int it = 0; it < iters; it++) {
 #pragma unroll
             for (int u = 0; u < 8; u++)
 #pragma unroll
-                for (int c = 0; c < CH; c++) x[c] = fma2(x[c], m, a);
+                for (int c = 0; c < CH; c++) {
+                    if (MODE == 1) x[c] = fma2(x[c], m, a);
+                    if (MODE == 3 || MODE == 5) x[c] = fma2(x[(c + 1) % CH], x[(c + 2) % CH], x[c]);
+                    if (MODE == 4) x[c] = fma2(x[(c + 1) % CH], pk(sc, sc), x[c]);
+                    if (MODE == 6) x[c] = add2(x[(c + 1) % CH], x[c]);
+                    if (MODE == 5 && (c & 1)) {
+                        float lo, hi;
+                        upk(x[c], lo, hi);
+                        mn = fminf(mn, lo);
+                    }
+                }
         }
-        float s = 0;
+        float s = mn;
 #pragma unroll
         for (int c = 0; c < CH; c++) {
             float lo, hi;

@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libsapporo.so")
+LIB_PATH = os.environ.get("G6_B200_LIB", os.path.join(HERE, "csrc", "libsapporo.so"))
 
 # Every symbol include/g6_b200.h declares (checked by tests/test_abi.py).
 G6_SYMBOLS = [
