@@ -276,8 +276,7 @@ const VariantInfo &variant_info(int v)
 int choose_variant(int ni)
 {
     if (G.variant != V_AUTO) return G.variant;
-    if (ni > 1536) return V_P4;
-    if (ni > 384) return V_P2;
+    if (ni > 384) return V_P2;   // measured: P2 (2 CTAs/SM) >= P4 (1 CTA/SM) at every size
     if (ni > 48) return V_P2W;
     if (ni > 4) return V_W1;
     return V_T1;

@@ -48,7 +48,7 @@ def test_golden_full_sweep_all_variants(g6, golden_dir, name, variant):
     check_nn(out["nn"], g["nn"], g["ids"], g["pos"], g["pos"])
     out2 = g6.calc(g["ids"], g["pos"], g["vel"], float(g["eps2"]), want_nn=False)   # lasthalf path
     check_forces(out2, g, what="%s v%d lasthalf" % (name, variant))
-    assert rel_vec_err(out2["acc"], out["acc"]).max() < 5e-7
+    assert rel_vec_err(out2["acc"], out["acc"]).max() < 1e-6
 
 
 def test_refine_switch(g6, golden_dir):
