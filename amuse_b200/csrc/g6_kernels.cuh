@@ -22,7 +22,7 @@ constexpr int THREADS = 256;   // threads per force CTA (8 warps)
 constexpr int TILE = 256;      // j-particles per shared-memory stage
 constexpr int STAGES = 3;      // TMA bulk-copy pipeline depth
 #ifndef G6_FLUSH
-#define G6_FLUSH 64
+#define G6_FLUSH 16
 #endif
 #ifndef G6_UNROLL
 #define G6_UNROLL 2
