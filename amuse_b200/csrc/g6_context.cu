@@ -46,6 +46,8 @@ enum Variant {
     V_P4 = 6,    // packed f32x2, 4 i/thread, 256 i-slots (IB 1024)
     V_P2 = 7,    // packed f32x2, 2 i/thread, 256 i-slots (IB 512)
     V_P2W = 8,   // packed f32x2, 2 i/thread, 32 i-slots x 8 j-slots (IB 64)
+    V_F4 = 9,    // speculative (mask-free groups + verification), packed, 4 i/thread (IB 1024)
+    V_F2 = 10,   // speculative, packed, 2 i/thread (IB 512)
     V_COUNT
 };
 
@@ -265,10 +267,33 @@ void launch_variant(const ForceArgs &a, dim3 grid, bool nn, bool list, cudaStrea
         launch_variant_nr<IPT, NI_SLOTS, PACKED, false, MINB>(a, grid, nn, list, st);
 }
 
+template <int IPT, int MINB>
+void launch_fast(const ForceArgs &a, dim3 grid, bool nn, cudaStream_t st)
+{
+    size_t smem = sizeof(ForceSmem);
+#define G6_LAUNCH(NN_, NR_)                                                                         \
+    do {                                                                                            \
+        auto kern = force_fast_kernel<IPT, NN_, NR_, MINB>;                                         \
+        static bool attr_set = false;                                                               \
+        if (!attr_set) {                                                                            \
+            CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            attr_set = true;                                                                        \
+        }                                                                                           \
+        kern<<<grid, THREADS, smem, st>>>(a);                                                       \
+    } while (0)
+    if (nn) {
+        if (G.refine) G6_LAUNCH(true, true); else G6_LAUNCH(true, false);
+    } else {
+        if (G.refine) G6_LAUNCH(false, true); else G6_LAUNCH(false, false);
+    }
+#undef G6_LAUNCH
+    CK(cudaGetLastError());
+}
+
 const VariantInfo &variant_info(int v)
 {
     static const VariantInfo info[V_COUNT] = {
-        {0, 0}, {1024, 1}, {512, 2}, {256, 2}, {32, 2}, {4, 2}, {1024, 1}, {512, 2}, {64, 2},
+        {0, 0}, {1024, 1}, {512, 2}, {256, 2}, {32, 2}, {4, 2}, {1024, 1}, {512, 2}, {64, 2}, {1024, 1}, {512, 2},
     };
     return info[v];
 }
@@ -276,7 +301,7 @@ const VariantInfo &variant_info(int v)
 int choose_variant(int ni)
 {
     if (G.variant != V_AUTO) return G.variant;
-    if (ni > 384) return V_P2;   // measured: P2 (2 CTAs/SM) >= P4 (1 CTA/SM) at every size
+    if (ni > 384) return V_F2;
     if (ni > 48) return V_P2W;
     if (ni > 4) return V_W1;
     return V_T1;
@@ -288,6 +313,8 @@ void launch_force(int nj, int ni, const float4 *iA, const float4 *iB, const floa
 {
     if (nj > G.capacity) nj = G.capacity;
     int v = choose_variant(ni);
+    if (list && v == V_F4) v = V_P4;   // neighbour lists test every pair against h2: masked kernels
+    if (list && v == V_F2) v = V_P2;
     const VariantInfo &vi = variant_info(v);
     int n_iblocks = (ni + vi.ib - 1) / vi.ib;
     int ntiles = (nj + TILE - 1) / TILE;
@@ -337,6 +364,8 @@ void launch_force(int nj, int ni, const float4 *iA, const float4 *iB, const floa
         case V_P4: launch_variant<4, 256, true, 1>(a, grid, nn, list, G.stream); break;
         case V_P2: launch_variant<2, 256, true, 2>(a, grid, nn, list, G.stream); break;
         case V_P2W: launch_variant<2, 32, true, 2>(a, grid, nn, list, G.stream); break;
+        case V_F4: launch_fast<4, 1>(a, grid, nn, G.stream); break;
+        case V_F2: launch_fast<2, 2>(a, grid, nn, G.stream); break;
         default:
             fprintf(stderr, "g6_b200: FATAL unknown force variant %d\n", v);
             exit(-1);
@@ -824,6 +853,7 @@ double g6x_time_predictor(int nj, int reps)
     CK(cudaEventRecord(e1, G.stream));
     CK(cudaEventSynchronize(e1));
     G.launches += reps + 3;
+    G.predicted_nj = -1;  // slots >= nj of the last tile were parked: predict again before the next force
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, e0, e1));
     cudaEventDestroy(e0);

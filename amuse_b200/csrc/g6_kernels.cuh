@@ -82,10 +82,14 @@ __global__ void scatter_kernel(int n, const JUpdate *__restrict__ up, JState s)
 
 // Hermite predictor (jdata.cc:726-747) in FP64, output split to double-single.
 // Algorithmic traffic: 112 B read + 48 B written per j.
-__global__ void predict_kernel(int n, double ti, JState s)
+// One CTA = one j-tile (TILE = 256 slots; the arrays are padded to whole tiles).  The CTA also
+// records the id range of its massive particles in the spare .w lanes of the tile's first two C
+// entries (C[tile*256].w = min id, C[tile*256+1].w = max id, as int bits): the force kernel uses
+// it to decide per tile whether the self-exclusion masks can be skipped.
+__global__ void __launch_bounds__(TILE) predict_kernel(int n, double ti, JState s)
 {
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
+    __shared__ int sh_lo[TILE / 32], sh_hi[TILE / 32];
+    const int j = blockIdx.x * TILE + threadIdx.x;   // always < capacity
     const double2 q0 = s.q[0][j], q1 = s.q[1][j], q2 = s.q[2][j], q3 = s.q[3][j], q4 = s.q[4][j], q5 = s.q[5][j],
                   q6 = s.q[6][j];
     const double x = q0.x, y = q0.y, z = q1.x, tj = q1.y, vx = q2.x, vy = q2.y, vz = q3.x;
@@ -102,15 +106,34 @@ __global__ void predict_kernel(int n, double ti, JState s)
         qy = vy + dt * (ay + 0.5 * dt * jy);
         qz = vz + dt * (az + 0.5 * dt * jz);
     }
-    if (!(m > TINYF)) {  // massless or never-set slot: park it (idata.cc:208)
+    const bool massive = (j < n) && (m > TINYF);
+    if (!massive) {  // massless or never-set slot: park it (idata.cc:208)
         px = py = pz = (double)FAR_AWAY;
         qx = qy = qz = 0.0;
     }
+    int lo = __reduce_min_sync(0xffffffffu, massive ? id : 0x7fffffff);
+    int hi = __reduce_max_sync(0xffffffffu, massive ? id : (int)0x80000000);
+    if ((threadIdx.x & 31) == 0) {
+        sh_lo[threadIdx.x >> 5] = lo;
+        sh_hi[threadIdx.x >> 5] = hi;
+    }
+    __syncthreads();
+    float cw = 0.f;
+    if (threadIdx.x < 2) {
+#pragma unroll
+        for (int w = 0; w < TILE / 32; w++) {
+            lo = min(lo, sh_lo[w]);
+            hi = max(hi, sh_hi[w]);
+        }
+        cw = __int_as_float(threadIdx.x == 0 ? lo : hi);
+    }
+    // slots in [n, end of tile) are written too (parked): the tile's id range lives in its first two
+    // entries and the force kernel bounds its j loop by nj anyway
     float xh = (float)px, yh = (float)py, zh = (float)pz;
     float xl = (float)(px - (double)xh), yl = (float)(py - (double)yh), zl = (float)(pz - (double)zh);
-    s.A[j] = make_float4(xh, yh, zh, m);
+    s.A[j] = make_float4(xh, yh, zh, massive ? m : 0.f);
     s.B[j] = make_float4(xl, yl, zl, __int_as_float(id));
-    s.C[j] = make_float4((float)qx, (float)qy, (float)qz, 0.f);
+    s.C[j] = make_float4((float)qx, (float)qy, (float)qz, cw);
 }
 
 // i-block packing for device-resident callers: double -> double-single.
@@ -289,7 +312,7 @@ struct Acc7P {
     u64 ax, ay, az, jx, jy, jz, pot;
 };
 
-template <bool NN, bool LIST, bool NR>
+template <bool NN, bool LIST, bool NR, bool TRACKJ = true>
 __device__ __forceinline__ void interact2(const float4 a, const float4 b, const float4 c, int jaddr, const IPair &I,
                                           u64 eps2p, Acc7P &s, float &r2min0, int &jmin0, float &r2min1,
                                           int &jmin1, int i_global0, const ForceArgs &p)
@@ -332,13 +355,18 @@ __device__ __forceinline__ void interact2(const float4 a, const float4 b, const 
     if (NN) {
         float n0 = ok0 ? r20 : __int_as_float(0x7f800000);
         float n1 = ok1 ? r21 : __int_as_float(0x7f800000);
-        if (n0 < r2min0) {
-            r2min0 = n0;
-            jmin0 = jaddr;
-        }
-        if (n1 < r2min1) {
-            r2min1 = n1;
-            jmin1 = jaddr;
+        if (!TRACKJ) {   // the speculative kernel keeps only the minimum and finds j afterwards
+            r2min0 = fminf(r2min0, n0);
+            r2min1 = fminf(r2min1, n1);
+        } else {
+            if (n0 < r2min0) {
+                r2min0 = n0;
+                jmin0 = jaddr;
+            }
+            if (n1 < r2min1) {
+                r2min1 = n1;
+                jmin1 = jaddr;
+            }
         }
     }
     if (LIST) {
@@ -349,6 +377,46 @@ __device__ __forceinline__ void interact2(const float4 a, const float4 b, const 
         if (ok1 && r21 <= I.h21) {
             int pos = atomicAdd(&p.ngb_cnt[i_global0 + 1], 1);
             if (pos < p.ngb_cap) p.ngb_list[(size_t)(i_global0 + 1) * p.ngb_cap + pos] = jid;
+        }
+    }
+}
+
+// Split reduction shared by the force kernels: the last CTA of an i-block (ticket) sums the
+// per-split partials in fixed order and writes the outputs.
+template <bool NN>
+__device__ __forceinline__ void reduce_splits(const ForceArgs &p, unsigned int *is_last, const int IB)
+{
+    const int tid = threadIdx.x;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        unsigned int tk = atomicAdd(&p.tickets[blockIdx.y], 1u);
+        *is_last = (tk == (unsigned)p.nsplit - 1u) ? 1u : 0u;
+        if (*is_last) p.tickets[blockIdx.y] = 0u;  // ready for the next launch
+    }
+    __syncthreads();
+    if (!*is_last) return;
+    __threadfence();
+    for (int il = tid; il < IB; il += THREADS) {
+        int i = blockIdx.y * IB + il;
+        if (i >= p.ni) continue;
+        double tot[7] = {0, 0, 0, 0, 0, 0, 0};
+        u64 kk = KEY_NONE;
+        for (int sp = 0; sp < p.nsplit; sp++) {
+            size_t o = (size_t)sp * p.ni_pad + i;
+            const double *r = p.part_sum + o * 7;
+#pragma unroll
+            for (int q = 0; q < 7; q++) tot[q] += __ldcg(r + q);
+            u64 ok = __ldcg(p.part_key + o);
+            kk = ok < kk ? ok : kk;
+        }
+#pragma unroll
+        for (int q = 0; q < 7; q++) p.out_sum[(size_t)i * 7 + q] = tot[q];
+        p.out_key[i] = kk;
+        if (NN) {
+            int id = -1;
+            if (kk != KEY_NONE) id = __float_as_int(p.jB[(int)(unsigned)(kk & 0xffffffffu) - p.j_offset].w);
+            p.out_nnid[i] = id;
         }
     }
 }
@@ -638,39 +706,302 @@ __global__ void __launch_bounds__(THREADS, MINB) force_kernel(const ForceArgs p)
     }
     if (single) return;
 
-    // ---- last CTA of this i-block sums the splits in fixed order ------------
-    __threadfence();
-    __syncthreads();
+    reduce_splits<NN>(p, &sm.is_last, IB);
+}
+
+// ---------------------------------------------------------------------------
+// Speculative force kernel (large i-blocks, packed FP32).
+//
+// The masks of the exact pair rule (skip equal ids; pot and the neighbour search only for
+// r2 > 2^-52) cost ~18 ALU-pipe instructions per packed pair and, on this chip, compete with the
+// FMA pipe for register-file read bandwidth (profiles/: FFMA2 with three distinct register
+// operands runs at 2/3 rate).  Almost no pair needs them, so the j stream is processed in groups
+// of GRP pairs WITHOUT masks, and each group is verified afterwards:
+//   * an equal-id pair can only occur in a tile whose id range [C[0].w, C[1].w] (written by
+//     predict_kernel) contains the id of one of the warp's i-particles -> such tiles take the
+//     masked path from the start;
+//   * a pair with r2 <= 2^-52 shows up in the running minimum of r2, which is tracked anyway for
+//     the nearest neighbour -> the group's FP32 partial sums are discarded and the group is redone
+//     with the masked pair function.
+// Results are therefore those of the masked rule for every input.  The nearest neighbour is kept
+// as (min r2, first group that lowered it) with one 3-input FMNMX per i per two j; the exact j is
+// found at the end by re-scanning that one group with the same r2 instruction sequence.
+// ---------------------------------------------------------------------------
+#ifndef G6_GRP
+#define G6_GRP 16
+#endif
+#ifndef G6_FUNROLL
+#define G6_FUNROLL 1
+#endif
+constexpr int GRP = G6_GRP;   // pairs per speculation/flush group (FP32 partial sums span one group)
+constexpr int FUNROLL = G6_FUNROLL;  // j-pairs unrolled in the mask-free loop
+
+__device__ __forceinline__ float min3f(float a, float b, float c)
+{
+    float d;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
+// Geometry shared by the fast path, the masked path and the neighbour re-scan: identical
+// instruction sequence, so r2 is bit-identical in all three.
+__device__ __forceinline__ void pair_geometry(const float4 a, const float4 b, const IPair &I, u64 &dx, u64 &dy, u64 &dz,
+                                              u64 &r2)
+{
+    dx = add2(add2(pk(a.x, a.x), I.nxh), add2(pk(b.x, b.x), I.nxl));
+    dy = add2(add2(pk(a.y, a.y), I.nyh), add2(pk(b.y, b.y), I.nyl));
+    dz = add2(add2(pk(a.z, a.z), I.nzh), add2(pk(b.z, b.z), I.nzl));
+    r2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
+}
+
+// One j against an i-pair, no masks: 38 packed FP32 operations + 2 MUFU.
+template <bool NR>
+__device__ __forceinline__ u64 interact2_fast(const float4 a, const float4 b, const float4 c, const IPair &I,
+                                              const u64 eps2p, Acc7P &s)
+{
+    u64 dx, dy, dz, r2;
+    pair_geometry(a, b, I, dx, dy, dz, r2);
+    const u64 dvx = add2(pk(c.x, c.x), I.nvx);
+    const u64 dvy = add2(pk(c.y, c.y), I.nvy);
+    const u64 dvz = add2(pk(c.z, c.z), I.nvz);
+    const u64 xv = fma2(dz, dvz, fma2(dy, dvy, mul2(dx, dvx)));
+    const u64 r2e = add2(r2, eps2p);
+    float e0, e1;
+    upk(r2e, e0, e1);
+    u64 rinv = pk(rsqrt_approx(e0), rsqrt_approx(e1));
+    if (NR) {
+        const u64 e = fma2(r2e, mul2(rinv, rinv), pk(-1.f, -1.f));
+        rinv = fma2(mul2(rinv, pk(-0.5f, -0.5f)), e, rinv);
+    }
+    const u64 rinv2 = mul2(rinv, rinv);
+    const u64 mrinv = mul2(pk(a.w, a.w), rinv);
+    const u64 mr3 = mul2(mrinv, rinv2);
+    const u64 a3 = mul2(mul2(xv, rinv2), pk(-3.f, -3.f));
+    s.ax = fma2(mr3, dx, s.ax);
+    s.ay = fma2(mr3, dy, s.ay);
+    s.az = fma2(mr3, dz, s.az);
+    s.jx = fma2(mr3, fma2(a3, dx, dvx), s.jx);
+    s.jy = fma2(mr3, fma2(a3, dy, dvy), s.jy);
+    s.jz = fma2(mr3, fma2(a3, dz, dvz), s.jz);
+    s.pot = add2(s.pot, mrinv);
+    return r2;
+}
+
+template <int IPT, bool NN, bool NR, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) force_fast_kernel(const ForceArgs p)
+{
+    static_assert(IPT % 2 == 0, "i-particles are processed in packed pairs");
+    static_assert(TILE % GRP == 0 && GRP % (2 * G6_FUNROLL) == 0, "group shape");
+    constexpr int NP = IPT / 2;
+    constexpr int IB = THREADS * IPT;
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    ForceSmem &sm = *reinterpret_cast<ForceSmem *>(smem_raw);
+    const int tid = threadIdx.x;
+
+    const int ntiles_total = (p.nj + TILE - 1) / TILE;
+    const int tile0 = blockIdx.x * p.tiles_per_split;
+    int ntiles = ntiles_total - tile0;
+    if (ntiles > p.tiles_per_split) ntiles = p.tiles_per_split;
+    if (ntiles < 0) ntiles = 0;
+
     if (tid == 0) {
-        unsigned int tk = atomicAdd(&p.tickets[blockIdx.y], 1u);
-        sm.is_last = (tk == (unsigned)p.nsplit - 1u) ? 1u : 0u;
-        if (sm.is_last) p.tickets[blockIdx.y] = 0u;  // ready for the next launch
+        for (int s = 0; s < STAGES; s++) mbar_init(&sm.full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (!sm.is_last) return;
-    __threadfence();
-    for (int il = tid; il < IB; il += THREADS) {
-        int i = blockIdx.y * IB + il;
-        if (i >= p.ni) continue;
-        double tot[7] = {0, 0, 0, 0, 0, 0, 0};
-        u64 kk = KEY_NONE;
-        for (int sp = 0; sp < p.nsplit; sp++) {
-            size_t o = (size_t)sp * p.ni_pad + i;
-            const double *r = p.part_sum + o * 7;
-#pragma unroll
-            for (int q = 0; q < 7; q++) tot[q] += __ldcg(r + q);
-            u64 ok = __ldcg(p.part_key + o);
-            kk = ok < kk ? ok : kk;
-        }
-#pragma unroll
-        for (int q = 0; q < 7; q++) p.out_sum[(size_t)i * 7 + q] = tot[q];
-        p.out_key[i] = kk;
-        if (NN) {
-            int id = -1;
-            if (kk != KEY_NONE) id = __float_as_int(p.jB[(int)(unsigned)(kk & 0xffffffffu) - p.j_offset].w);
-            p.out_nnid[i] = id;
+    constexpr uint32_t STAGE_BYTES = 3u * TILE * sizeof(float4);
+    if (tid == 0) {
+        for (int s = 0; s < STAGES && s < ntiles; s++) {
+            size_t off = (size_t)(tile0 + s) * TILE;
+            mbar_expect_tx(&sm.full[s], STAGE_BYTES);
+            bulk_g2s(sm.A[s], p.jA + off, TILE * sizeof(float4), &sm.full[s]);
+            bulk_g2s(sm.B[s], p.jB + off, TILE * sizeof(float4), &sm.full[s]);
+            bulk_g2s(sm.C[s], p.jC + off, TILE * sizeof(float4), &sm.full[s]);
         }
     }
+
+    // ---- register-resident i-pairs: i = block base + 2*tid + {0,1} + q*2*THREADS -------------
+    IPair IP[NP];
+    int iid[IPT];
+    auto i_of = [&](int k) -> int { return blockIdx.y * IB + (tid * 2 + (k & 1)) + (k >> 1) * (2 * THREADS); };
+#pragma unroll
+    for (int q = 0; q < NP; q++) {
+        float4 a[2], b[2], c[2];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int i = i_of(2 * q + h);
+            a[h] = make_float4(0.f, 0.f, 0.f, -1.f);
+            b[h] = make_float4(0.f, 0.f, 0.f, __int_as_float(0x80000000));
+            c[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < p.ni) {
+                a[h] = p.iA[i];
+                b[h] = p.iB[i];
+                c[h] = p.iC[i];
+            }
+            iid[2 * q + h] = __float_as_int(b[h].w);
+        }
+        IP[q].nxh = pk(-a[0].x, -a[1].x); IP[q].nyh = pk(-a[0].y, -a[1].y); IP[q].nzh = pk(-a[0].z, -a[1].z);
+        IP[q].nxl = pk(-b[0].x, -b[1].x); IP[q].nyl = pk(-b[0].y, -b[1].y); IP[q].nzl = pk(-b[0].z, -b[1].z);
+        IP[q].nvx = pk(-c[0].x, -c[1].x); IP[q].nvy = pk(-c[0].y, -c[1].y); IP[q].nvz = pk(-c[0].z, -c[1].z);
+        IP[q].id0 = iid[2 * q]; IP[q].id1 = iid[2 * q + 1];
+        IP[q].h20 = a[0].w; IP[q].h21 = a[1].w;
+    }
+
+    double D[IPT][7];
+    float rmin[IPT], rprev[IPT];   // running minimum of r2 (masked rule), and its value at the last group boundary
+    int jgrp[IPT];                 // first j of the group that last lowered it (local address), -1: none
+#pragma unroll
+    for (int k = 0; k < IPT; k++) {
+#pragma unroll
+        for (int q = 0; q < 7; q++) D[k][q] = 0.0;
+        rmin[k] = rprev[k] = __int_as_float(0x7f800000);
+        jgrp[k] = -1;
+    }
+    const float eps2 = p.eps2 + TINYF;   // the reference softens by eps2 + 2^-52 (idata.cc:216)
+    const u64 eps2p = pk(eps2, eps2);
+
+    for (int t = 0; t < ntiles; t++) {
+        const int s = t % STAGES;
+        const uint32_t phase = (uint32_t)(t / STAGES) & 1u;
+        while (!mbar_try_wait(&sm.full[s], phase)) {
+        }
+        const int jtile = (tile0 + t) * TILE;
+        int cnt = p.nj - jtile;
+        if (cnt > TILE) cnt = TILE;
+        const float4 *tA = sm.A[s], *tB = sm.B[s], *tC = sm.C[s];
+
+        // may this warp meet an equal-id pair in this tile?
+        const int idlo = __float_as_int(tC[0].w), idhi = __float_as_int(tC[1].w);
+        bool hit = false;
+#pragma unroll
+        for (int k = 0; k < IPT; k++) hit |= (iid[k] >= idlo) & (iid[k] <= idhi);
+        const bool tile_masked = __any_sync(0xffffffffu, hit) || (cnt < TILE);
+
+        for (int jj0 = 0; jj0 < cnt; jj0 += GRP) {
+            Acc7P S[NP];
+            bool fast = !tile_masked;
+            if (fast) {
+#pragma unroll
+                for (int q = 0; q < NP; q++) S[q] = Acc7P{0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull};
+#pragma unroll FUNROLL
+                for (int u = 0; u < GRP; u += 2) {
+                    const int jj = jj0 + u;
+                    const float4 a0 = tA[jj], b0 = tB[jj], c0 = tC[jj];
+                    const float4 a1 = tA[jj + 1], b1 = tB[jj + 1], c1 = tC[jj + 1];
+#pragma unroll
+                    for (int q = 0; q < NP; q++) {
+                        const u64 ra = interact2_fast<NR>(a0, b0, c0, IP[q], eps2p, S[q]);
+                        const u64 rb = interact2_fast<NR>(a1, b1, c1, IP[q], eps2p, S[q]);
+                        float ra0, ra1, rb0, rb1;
+                        upk(ra, ra0, ra1);
+                        upk(rb, rb0, rb1);
+                        rmin[2 * q] = min3f(rmin[2 * q], ra0, rb0);
+                        rmin[2 * q + 1] = min3f(rmin[2 * q + 1], ra1, rb1);
+                    }
+                }
+                bool bad = false;
+#pragma unroll
+                for (int k = 0; k < IPT; k++) bad |= !(rmin[k] > TINYF);
+                if (__any_sync(0xffffffffu, bad)) {   // a coincident pair: redo the group with the masks
+                    fast = false;
+#pragma unroll
+                    for (int k = 0; k < IPT; k++) rmin[k] = rprev[k];
+                }
+            }
+            if (!fast) {
+#pragma unroll
+                for (int q = 0; q < NP; q++) S[q] = Acc7P{0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull};
+                const int jend = (jj0 + GRP < cnt) ? jj0 + GRP : cnt;
+                for (int jj = jj0; jj < jend; jj++) {
+                    const float4 a = tA[jj], b = tB[jj], c = tC[jj];
+                    int unused0 = 0, unused1 = 0;
+#pragma unroll
+                    for (int q = 0; q < NP; q++)
+                        interact2<true, false, NR, false>(a, b, c, 0, IP[q], eps2p, S[q], rmin[2 * q], unused0,
+                                                          rmin[2 * q + 1], unused1, 0, p);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < NP; q++) {
+                float lo, hi;
+                upk(S[q].ax, lo, hi); D[2 * q][0] += (double)lo; D[2 * q + 1][0] += (double)hi;
+                upk(S[q].ay, lo, hi); D[2 * q][1] += (double)lo; D[2 * q + 1][1] += (double)hi;
+                upk(S[q].az, lo, hi); D[2 * q][2] += (double)lo; D[2 * q + 1][2] += (double)hi;
+                upk(S[q].jx, lo, hi); D[2 * q][3] += (double)lo; D[2 * q + 1][3] += (double)hi;
+                upk(S[q].jy, lo, hi); D[2 * q][4] += (double)lo; D[2 * q + 1][4] += (double)hi;
+                upk(S[q].jz, lo, hi); D[2 * q][5] += (double)lo; D[2 * q + 1][5] += (double)hi;
+                upk(S[q].pot, lo, hi); D[2 * q][6] += (double)lo; D[2 * q + 1][6] += (double)hi;
+            }
+            if (NN) {
+#pragma unroll
+                for (int k = 0; k < IPT; k++) {
+                    if (rmin[k] < rprev[k]) jgrp[k] = jtile + jj0;
+                    rprev[k] = rmin[k];
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < IPT; k++) rprev[k] = rmin[k];
+            }
+        }
+
+        __syncthreads();  // everyone is done with stage s
+        if (tid == 0 && t + STAGES < ntiles) {
+            size_t off = (size_t)(tile0 + t + STAGES) * TILE;
+            mbar_expect_tx(&sm.full[s], STAGE_BYTES);
+            bulk_g2s(sm.A[s], p.jA + off, TILE * sizeof(float4), &sm.full[s]);
+            bulk_g2s(sm.B[s], p.jB + off, TILE * sizeof(float4), &sm.full[s]);
+            bulk_g2s(sm.C[s], p.jC + off, TILE * sizeof(float4), &sm.full[s]);
+        }
+    }
+
+    // ---- nearest neighbour: re-scan the one group that holds the minimum ---------------------
+    u64 key[IPT];
+#pragma unroll
+    for (int k = 0; k < IPT; k++) {
+        int jm = -1;
+        if (NN && jgrp[k] >= 0 && rmin[k] < 1.0e30f) {   // >= 1e30: only parked (massless) slots were seen
+            const int jend = (jgrp[k] + GRP < p.nj) ? jgrp[k] + GRP : p.nj;
+            for (int jj = jgrp[k]; jj < jend; jj++) {
+                const float4 a = p.jA[jj], b = p.jB[jj];
+                u64 dx, dy, dz, r2;
+                pair_geometry(a, b, IP[k >> 1], dx, dy, dz, r2);
+                float r0, r1;
+                upk(r2, r0, r1);
+                const float r = (k & 1) ? r1 : r0;
+                if (__float_as_int(b.w) != iid[k] && r > TINYF && r == rmin[k]) {
+                    jm = jj;
+                    break;
+                }
+            }
+        }
+        key[k] = (jm >= 0) ? make_key(rmin[k], jm + p.j_offset) : KEY_NONE;
+    }
+
+    // ---- totals -> global (final or per-split partial) -----------------------------------
+    const bool single = (p.nsplit == 1);
+#pragma unroll
+    for (int k = 0; k < IPT; k++) {
+        const int i = i_of(k);
+        if (i >= p.ni) continue;
+        if (single) {
+#pragma unroll
+            for (int q = 0; q < 7; q++) p.out_sum[(size_t)i * 7 + q] = D[k][q];
+            p.out_key[i] = key[k];
+            if (NN) {
+                int id = -1;
+                if (key[k] != KEY_NONE) id = __float_as_int(p.jB[(int)(unsigned)(key[k] & 0xffffffffu) - p.j_offset].w);
+                p.out_nnid[i] = id;
+            }
+        } else {
+            size_t o = (size_t)blockIdx.x * p.ni_pad + i;
+#pragma unroll
+            for (int q = 0; q < 7; q++) p.part_sum[o * 7 + q] = D[k][q];
+            p.part_key[o] = key[k];
+        }
+    }
+    if (single) return;
+    reduce_splits<NN>(p, &sm.is_last, IB);
 }
 
 // After a min-reduction of keys over ranks (each rank holds a j-shard).

@@ -15,7 +15,7 @@ from helpers import TOL, check_forces, check_nn, error_report, rel_err, rel_vec_
 
 pytestmark = pytest.mark.gpu
 
-VARIANTS = [1, 2, 3, 4, 5, 6, 7, 8]   # see DESIGN.md; 0 = auto
+VARIANTS = [1, 2, 3, 4, 5, 6, 7, 8, 9, 10]   # see DESIGN.md; 0 = auto; 9, 10 = speculative kernels
 
 
 def _O():
@@ -144,6 +144,46 @@ def test_massless_coincident_and_unset_slots(g6):
     out = g6.calc(ids[:40], x[:40], v[:40], 1e-4, nj=20300)
     ref = O.force(x[:40], v[:40], m, x, v, 1e-4, iid=ids[:40], jid=ids)
     check_forces(out, ref, what="holes")
+
+
+@pytest.mark.parametrize("variant", [9, 10])
+def test_speculative_kernel_equals_masked_kernel(g6, variant):
+    """The speculative kernels (mask-free groups + verification) must return what the
+    masked pair rule returns on inputs that exercise every fallback: ids shuffled against addresses
+    (every tile's id range contains every i), coincident particles and a self pair that is NOT at
+    r = 0 (host-predicted i), massless particles, a ragged last tile, and nearest neighbours that sit
+    in the first, a middle and the last group of the j range."""
+    O = _O()
+    rng = np.random.RandomState(77)
+    n = 3000                                   # 11 full tiles + a ragged one
+    m, x, v = P.new_plummer_model(n, seed=21)
+    m = m.copy(); x = x.copy(); v = v.copy()
+    m[100:110] = 0.0
+    x[500] = x[1500]                           # coincident pair across tiles
+    x[1234] = x[1233]                          # coincident pair inside one group
+    xn = x.copy()                              # near-coincident variants (r2 < 2^-52 but not 0): only with
+    xn[2999] = xn[0] + 1e-9                    # softening, where such a pair carries no weight (without it
+    xn[1234] = xn[1233] + np.array([3e-9, 0, 0])  # its force is ~1e11 and not representable to 1e-6)
+    for ids in (np.arange(1, n + 1, dtype=np.int32), rng.permutation(n).astype(np.int32) + 5):
+        for eps2 in (0.0, 1e-4):
+            xj = x if eps2 == 0.0 else xn
+            _fresh(g6, ids, m, xj, v)
+            # with softening i is also "predicted on the host": the self pair is not exactly at r = 0
+            xi = xj if eps2 == 0.0 else xj + 1e-12
+            ref = O.force(xi, v, m, xj, v, eps2, iid=ids, jid=ids)
+            g6.set_variant(7)
+            masked = g6.calc(ids, xi, v, eps2)
+            g6.set_variant(variant)
+            out = g6.calc(ids, xi, v, eps2)
+            out_nonn = g6.calc(ids, xi, v, eps2, want_nn=False)
+            g6.set_variant(0)
+            check_forces(out, ref, what="speculative v%d eps2=%g" % (variant, eps2))
+            check_nn(out["nn"], ref["nn"], ids, xi, xj)
+            assert np.array_equal(out["nn"], masked["nn"])
+            # same arithmetic per pair, different summation grouping only
+            assert rel_vec_err(out["acc"], masked["acc"]).max() < 5e-7
+            assert rel_err(out["pot"], masked["pot"]).max() < 5e-7
+            assert np.array_equal(out_nonn["acc"], out["acc"]) and np.array_equal(out_nonn["pot"], out["pot"])
 
 
 def test_j_update_visible_and_last_write_wins(g6):
