@@ -733,6 +733,9 @@ __global__ void __launch_bounds__(THREADS, MINB) force_kernel(const ForceArgs p)
 #ifndef G6_FUNROLL
 #define G6_FUNROLL 1
 #endif
+#ifndef G6_DUAL
+#define G6_DUAL 0   // 0: one FP32 partial-sum set per group; k: two sets (even/odd j) in kernels with IPT >= k
+#endif
 constexpr int GRP = G6_GRP;   // pairs per speculation/flush group (FP32 partial sums span one group)
 constexpr int FUNROLL = G6_FUNROLL;  // j-pairs unrolled in the mask-free loop
 
@@ -754,7 +757,7 @@ __device__ __forceinline__ void pair_geometry(const float4 a, const float4 b, co
     r2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
 }
 
-// One j against an i-pair, no masks: 38 packed FP32 operations + 2 MUFU.
+// One j against an i-pair, no masks: 38 packed FP32 operations + 2 MUFU.  Accumulates -acc, -jerk, +pot.
 template <bool NR>
 __device__ __forceinline__ u64 interact2_fast(const float4 a, const float4 b, const float4 c, const IPair &I,
                                               const u64 eps2p, Acc7P &s)
@@ -768,21 +771,32 @@ __device__ __forceinline__ u64 interact2_fast(const float4 a, const float4 b, co
     const u64 r2e = add2(r2, eps2p);
     float e0, e1;
     upk(r2e, e0, e1);
-    u64 rinv = pk(rsqrt_approx(e0), rsqrt_approx(e1));
+    const u64 y0 = pk(rsqrt_approx(e0), rsqrt_approx(e1));
+    // rinv2 and mr3 carry a MINUS sign here (the caller subtracts the acc/jerk partial sums): with
+    // x = r2 + eps2 and one Newton step from y0 = MUFU.RSQ(x),
+    //   e2 = x*y0^2 - 2 ;  -1/r^2 = y0^2 * e2  (Newton for 1/x from y0^2) ;  1/r = y0 * (0.5 - e2/2)
+    // -- no instruction of the step reads three distinct register pairs.
+    u64 rinv2, mrinv;
     if (NR) {
-        const u64 e = fma2(r2e, mul2(rinv, rinv), pk(-1.f, -1.f));
-        rinv = fma2(mul2(rinv, pk(-0.5f, -0.5f)), e, rinv);
+        const u64 yy = mul2(y0, y0);
+        const u64 e2 = fma2(r2e, yy, pk(-2.f, -2.f));
+        rinv2 = mul2(yy, e2);
+        mrinv = mul2(mul2(pk(a.w, a.w), y0), fma2(e2, pk(-0.5f, -0.5f), pk(0.5f, 0.5f)));
+    } else {
+        rinv2 = mul2(y0, mul2(y0, pk(-1.f, -1.f)));
+        mrinv = mul2(pk(a.w, a.w), y0);
     }
-    const u64 rinv2 = mul2(rinv, rinv);
-    const u64 mrinv = mul2(pk(a.w, a.w), rinv);
-    const u64 mr3 = mul2(mrinv, rinv2);
-    const u64 a3 = mul2(mul2(xv, rinv2), pk(-3.f, -3.f));
+    const u64 mr3 = mul2(mrinv, rinv2);                          // = -m/r^3
+    const u64 a3 = mul2(mul2(xv, rinv2), pk(3.f, 3.f));          // = -3 x.v/r^2
+    const u64 tx = fma2(a3, dx, dvx);
+    const u64 ty = fma2(a3, dy, dvy);
+    const u64 tz = fma2(a3, dz, dvz);
     s.ax = fma2(mr3, dx, s.ax);
     s.ay = fma2(mr3, dy, s.ay);
     s.az = fma2(mr3, dz, s.az);
-    s.jx = fma2(mr3, fma2(a3, dx, dvx), s.jx);
-    s.jy = fma2(mr3, fma2(a3, dy, dvy), s.jy);
-    s.jz = fma2(mr3, fma2(a3, dz, dvz), s.jz);
+    s.jx = fma2(mr3, tx, s.jx);
+    s.jy = fma2(mr3, ty, s.jy);
+    s.jz = fma2(mr3, tz, s.jz);
     s.pot = add2(s.pot, mrinv);
     return r2;
 }
@@ -790,6 +804,7 @@ __device__ __forceinline__ u64 interact2_fast(const float4 a, const float4 b, co
 template <int IPT, bool NN, bool NR, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) force_fast_kernel(const ForceArgs p)
 {
+    constexpr bool DUAL = (G6_DUAL != 0) && (IPT >= G6_DUAL);
     static_assert(IPT % 2 == 0, "i-particles are processed in packed pairs");
     static_assert(TILE % GRP == 0 && GRP % (2 * G6_FUNROLL) == 0, "group shape");
     constexpr int NP = IPT / 2;
@@ -882,8 +897,14 @@ __global__ void __launch_bounds__(THREADS, MINB) force_fast_kernel(const ForceAr
             Acc7P S[NP];
             bool fast = !tile_masked;
             if (fast) {
+                // DUAL: even and odd j of the group go to separate FP32 partial sums (each spans GRP/2
+                // pairs, which is what bounds the rounding error of a sum dominated by one close pair)
+                Acc7P S1[DUAL ? NP : 1];
 #pragma unroll
-                for (int q = 0; q < NP; q++) S[q] = Acc7P{0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull};
+                for (int q = 0; q < NP; q++) {
+                    S[q] = Acc7P{0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull};
+                    if (DUAL) S1[q] = Acc7P{0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull};
+                }
 #pragma unroll FUNROLL
                 for (int u = 0; u < GRP; u += 2) {
                     const int jj = jj0 + u;
@@ -892,12 +913,21 @@ __global__ void __launch_bounds__(THREADS, MINB) force_fast_kernel(const ForceAr
 #pragma unroll
                     for (int q = 0; q < NP; q++) {
                         const u64 ra = interact2_fast<NR>(a0, b0, c0, IP[q], eps2p, S[q]);
-                        const u64 rb = interact2_fast<NR>(a1, b1, c1, IP[q], eps2p, S[q]);
+                        const u64 rb = interact2_fast<NR>(a1, b1, c1, IP[q], eps2p, DUAL ? S1[q] : S[q]);
                         float ra0, ra1, rb0, rb1;
                         upk(ra, ra0, ra1);
                         upk(rb, rb0, rb1);
                         rmin[2 * q] = min3f(rmin[2 * q], ra0, rb0);
                         rmin[2 * q + 1] = min3f(rmin[2 * q + 1], ra1, rb1);
+                    }
+                }
+                if (DUAL) {
+#pragma unroll
+                    for (int q = 0; q < NP; q++) {
+                        S[q].ax = add2(S[q].ax, S1[q].ax); S[q].ay = add2(S[q].ay, S1[q].ay);
+                        S[q].az = add2(S[q].az, S1[q].az); S[q].jx = add2(S[q].jx, S1[q].jx);
+                        S[q].jy = add2(S[q].jy, S1[q].jy); S[q].jz = add2(S[q].jz, S1[q].jz);
+                        S[q].pot = add2(S[q].pot, S1[q].pot);
                     }
                 }
                 bool bad = false;
@@ -922,15 +952,16 @@ __global__ void __launch_bounds__(THREADS, MINB) force_fast_kernel(const ForceAr
                                                           rmin[2 * q + 1], unused1, 0, p);
                 }
             }
+            const double sg = fast ? -1.0 : 1.0;   // the mask-free pair function accumulates -acc, -jerk
 #pragma unroll
             for (int q = 0; q < NP; q++) {
                 float lo, hi;
-                upk(S[q].ax, lo, hi); D[2 * q][0] += (double)lo; D[2 * q + 1][0] += (double)hi;
-                upk(S[q].ay, lo, hi); D[2 * q][1] += (double)lo; D[2 * q + 1][1] += (double)hi;
-                upk(S[q].az, lo, hi); D[2 * q][2] += (double)lo; D[2 * q + 1][2] += (double)hi;
-                upk(S[q].jx, lo, hi); D[2 * q][3] += (double)lo; D[2 * q + 1][3] += (double)hi;
-                upk(S[q].jy, lo, hi); D[2 * q][4] += (double)lo; D[2 * q + 1][4] += (double)hi;
-                upk(S[q].jz, lo, hi); D[2 * q][5] += (double)lo; D[2 * q + 1][5] += (double)hi;
+                upk(S[q].ax, lo, hi); D[2 * q][0] += sg * (double)lo; D[2 * q + 1][0] += sg * (double)hi;
+                upk(S[q].ay, lo, hi); D[2 * q][1] += sg * (double)lo; D[2 * q + 1][1] += sg * (double)hi;
+                upk(S[q].az, lo, hi); D[2 * q][2] += sg * (double)lo; D[2 * q + 1][2] += sg * (double)hi;
+                upk(S[q].jx, lo, hi); D[2 * q][3] += sg * (double)lo; D[2 * q + 1][3] += sg * (double)hi;
+                upk(S[q].jy, lo, hi); D[2 * q][4] += sg * (double)lo; D[2 * q + 1][4] += sg * (double)hi;
+                upk(S[q].jz, lo, hi); D[2 * q][5] += sg * (double)lo; D[2 * q + 1][5] += sg * (double)hi;
                 upk(S[q].pot, lo, hi); D[2 * q][6] += (double)lo; D[2 * q + 1][6] += (double)hi;
             }
             if (NN) {

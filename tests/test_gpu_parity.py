@@ -97,7 +97,7 @@ def test_ragged_sizes(g6, ni, nj):
     k = min(ni, nj) // 2                          # ... and some genuine members
     ipos[:k], ivel[:k], iid[:k] = x[:k], v[:k], ids[:k]
     out = g6.calc(iid, ipos, ivel, 1e-4, nj=nj)
-    ref = O.force(ipos, ivel, m, x, v, 1e-4, iid=iid, jid=ids)
+    ref = O.force(ipos, ivel, m, x, v, 1e-4, iid=iid, jid=ids, scales=(ni > 1 and nj > 1))
     if nj == 1 and k == 1:
         assert np.all(out["acc"][0] == 0) and out["pot"][0] == 0 and out["nn"][0] == -1
         out = {kk: vv[1:] for kk, vv in out.items()}
