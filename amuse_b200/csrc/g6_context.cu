@@ -64,6 +64,7 @@ struct Context {
     int npipes = 16384;
     int ngb_cap = 1024;
     int variant = V_AUTO;
+    int force_nsplit = 0;
     int refine = 1;        // Newton-refined rsqrt (accuracy first); 0 = raw MUFU.RSQ
     bool ext_stream = false;
     int j_offset = 0;
@@ -94,6 +95,7 @@ struct Context {
     int *h_nnid = nullptr;    // pinned
     // device-resident entry point scratch
     float4 *d_i2 = nullptr;
+    int i2_cap = 0;
     // partial workspace
     double *part_sum = nullptr;
     u64 *part_key = nullptr;
@@ -319,10 +321,13 @@ void launch_force(int nj, int ni, const float4 *iA, const float4 *iB, const floa
     int n_iblocks = (ni + vi.ib - 1) / vi.ib;
     int ntiles = (nj + TILE - 1) / TILE;
     if (ntiles < 1) ntiles = 1;
-    // j-splits: pick the split count that minimises (waves x tiles per CTA), i.e. fills whole
-    // waves of resident CTAs; c0 ~ fixed per-CTA cost (prologue + reduction) in tile units.
+    // j-splits: pick the split count that minimises the modelled makespan
+    //     (waves + w0) x (tiles per CTA + c0)
+    // c0 ~ fixed per-CTA cost (prologue + reduction) in tile units; w0 = 0.06 is measured: SMs do not
+    // all run at the same speed, so one wave of long CTAs ends ~6 % later than four waves of short
+    // ones that the hardware scheduler balances (profiles/r01_grid_granularity.txt).
     const int slots = G.sm_count * vi.ctas_per_sm;
-    const double c0 = 1.5;
+    const double c0 = 1.5, w0 = 0.06;
     int best_ns = 1;
     double best_cost = 1e300;
     int max_ns = std::min(ntiles, std::max(1, 4 * slots / n_iblocks));
@@ -331,13 +336,14 @@ void launch_force(int nj, int ni, const float4 *iA, const float4 *iB, const floa
         int ns_ = (ntiles + tps_ - 1) / tps_;
         long long ctas = (long long)ns_ * n_iblocks;
         long long waves = (ctas + slots - 1) / slots;
-        double cost = (double)waves * (tps_ + c0);
+        double cost = ((double)waves + w0) * (tps_ + c0);
         if (cost < best_cost * 0.999) {
             best_cost = cost;
             best_ns = ns_;
         }
     }
     int nsplit = best_ns;
+    if (G.force_nsplit > 0) nsplit = std::min(G.force_nsplit, ntiles);   // G6_B200_NSPLIT: experiments only
     int tps = (ntiles + nsplit - 1) / nsplit;
     nsplit = (ntiles + tps - 1) / tps;
 
@@ -384,7 +390,7 @@ void free_all()
     dev_free(G.part_sum); dev_free(G.part_key); dev_free(G.tickets);
     dev_free(G.d_ngb_cnt); dev_free(G.d_ngb_list);
     host_free(G.h_ngb_cnt); host_free(G.h_ngb_list);
-    G.capacity = 0; G.nj_hi = 0; G.up_cap = 0; G.up_n = 0; G.part_records = 0;
+    G.capacity = 0; G.nj_hi = 0; G.up_cap = 0; G.up_n = 0; G.part_records = 0; G.i2_cap = 0;
     G.slot_of_addr.clear();
     G.predicted_nj = -1; G.j_dirty = false; G.pending = false;
     G.ngb_valid = G.ngb_fetched = false;
@@ -417,6 +423,24 @@ void stage_j(int address, int index, double tj, double mass, const double *j6, c
     u.addr = address;
     u.pad[0] = u.pad[1] = u.pad[2] = 0;
     if (address + 1 > G.nj_hi) G.nj_hi = address + 1;
+}
+
+// Chunk size of the device path: unlike the ABI path it is not tied to g6_npipes().  For big
+// i-sets pick the chunk whose i-blocks x j-splits fill the resident CTA slots exactly
+// (148 SMs x 2 CTAs = 296 = 37 i-blocks x 8 splits of the speculative kernel), so that no
+// slot idles in a launch; small i-sets go out in one launch.
+int device_chunk(int ni)
+{
+    int chunk = G.npipes;
+    if (G.variant == V_AUTO && ni > G.npipes) {
+        const VariantInfo &vi = variant_info(V_F2);
+        const int slots = G.sm_count * vi.ctas_per_sm;
+        int split = 1;
+        for (int sdiv = 2; sdiv <= 16; sdiv++)
+            if (slots % sdiv == 0) split = sdiv;
+        chunk = vi.ib * (slots / split);
+    }
+    return chunk;
 }
 
 }  // namespace
@@ -467,9 +491,11 @@ int g6_open_(int *id)
     G.ngb_cap = std::max(1, env_int("G6_B200_NGB_CAP", 1024));
     G.variant = env_int("G6_B200_VARIANT", V_AUTO);
     G.refine = env_int("G6_B200_REFINE", 1);
+    G.force_nsplit = env_int("G6_B200_NSPLIT", 0);
     host_alloc(G.h_i, (size_t)3 * G.npipes);
     dev_alloc(G.d_i, (size_t)3 * G.npipes);
     dev_alloc(G.d_i2, (size_t)3 * G.npipes);
+    G.i2_cap = G.npipes;
     dev_alloc(G.d_sum, (size_t)7 * G.npipes);
     dev_alloc(G.d_key, (size_t)G.npipes);
     dev_alloc(G.d_nnid, (size_t)G.npipes);
@@ -779,9 +805,16 @@ int g6x_calc_device(int nj, int ni, const int *d_index, const double *d_xi, cons
         fprintf(stderr, "g6_b200: FATAL g6x_calc_device: neighbour lists are served by the g6 ABI path only\n");
         exit(-1);
     }
-    for (int i0 = 0; i0 < ni; i0 += G.npipes) {
-        int n = std::min(G.npipes, ni - i0);
-        float4 *A = G.d_i2, *B = G.d_i2 + G.npipes, *C = G.d_i2 + 2 * (size_t)G.npipes;
+    const int chunk = device_chunk(ni);
+    if (chunk > G.i2_cap) {
+        CK(cudaStreamSynchronize(G.stream));
+        dev_free(G.d_i2);
+        dev_alloc(G.d_i2, (size_t)3 * chunk);
+        G.i2_cap = chunk;
+    }
+    for (int i0 = 0; i0 < ni; i0 += chunk) {
+        int n = std::min(chunk, ni - i0);
+        float4 *A = G.d_i2, *B = G.d_i2 + G.i2_cap, *C = G.d_i2 + 2 * (size_t)G.i2_cap;
         pack_i_kernel<<<(n + 255) / 256, 256, 0, G.stream>>>(n, d_index + i0, d_xi + 3 * (size_t)i0,
                                                               d_vi + 3 * (size_t)i0, d_h2 ? d_h2 + i0 : nullptr, A, B,
                                                               C);
@@ -790,6 +823,12 @@ int g6x_calc_device(int nj, int ni, const int *d_index, const double *d_xi, cons
         launch_force(nj, n, A, B, C, (float)eps2, nn, false, d_sum + 7 * (size_t)i0, d_key + i0, d_nnid + i0);
     }
     return 0;
+}
+
+int g6x_device_chunk(int ni)
+{
+    require_open("g6x_device_chunk");
+    return device_chunk(ni);
 }
 
 int g6x_resolve_nn(int ni, const unsigned long long *d_key, int rank, int *d_nnid)

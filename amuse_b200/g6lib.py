@@ -27,7 +27,7 @@ G6_SYMBOLS = [
     "g6_read_neighbour_list", "g6_get_neighbour_list", "g6_set_neighbour_list_sort_mode",
     "g6_get_neighbour_list_sort_mode", "g6_set_overflow_flag_test_mode", "force_j_particle_send",
     "g6x_version", "g6x_set_stream", "g6x_set_refine", "g6x_set_j_offset", "g6x_set_j_particles", "g6x_predict",
-    "g6x_calc_device", "g6x_resolve_nn", "g6x_synchronize", "g6x_launch_count", "g6x_get_predicted",
+    "g6x_calc_device", "g6x_device_chunk", "g6x_resolve_nn", "g6x_synchronize", "g6x_launch_count", "g6x_get_predicted",
     "g6x_read_predicted", "g6x_time_predictor", "g6x_set_variant", "g6x_fp32_peak",
 ]
 
@@ -67,6 +67,7 @@ def load():
     L.g6x_predict.argtypes = [C.c_int, C.c_double]
     L.g6x_calc_device.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.g6x_device_chunk.argtypes = [C.c_int]
     L.g6x_resolve_nn.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p]
     L.g6x_launch_count.restype = C.c_longlong
     L.g6x_read_predicted.argtypes = [C.c_int, _dp, _dp]

@@ -165,6 +165,10 @@ int g6x_calc_device(int nj, int ni, const int *d_index, const double *d_xi,
                     const double *d_vi, const double *d_h2, double eps2,
                     int flags, double *d_sum, unsigned long long *d_key,
                     int *d_nnid);
+/* i-particles per kernel launch that g6x_calc_device uses for an i-set of ni (it
+ * picks the chunk whose i-blocks x j-splits fill the resident CTA slots exactly;
+ * g6_npipes_() only bounds the ABI path). */
+int g6x_device_chunk(int ni);
 /* After a min-reduction of d_key over ranks: d_nnid[i] = id of the winning j if
  * this rank owns it, else 0 (so a sum over ranks gives the id), -1 on rank 0
  * if there is no neighbour.  Mirrors idata.cc:308-313. */

@@ -14,7 +14,7 @@ from amuse_b200 import g6lib, plummer as P  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--n", type=int, default=262144)
-ap.add_argument("--ni", type=int, default=16384)
+ap.add_argument("--ni", default="16384", help="comma-separated i-block sizes")
 ap.add_argument("--variants", default="6,7")
 ap.add_argument("--refine", default="1,0")
 ap.add_argument("--reps", type=int, default=5)
@@ -30,7 +30,8 @@ L = g.L
 L.g6x_set_stream(C.c_void_p(torch.cuda.current_stream(dev).cuda_stream), 1)
 g.set_j_particles(ids, m, x, v)
 L.g6x_predict(a.n, 0.0)
-ni = a.ni
+nis = [int(t) for t in a.ni.split(",")]
+ni = max(nis)
 d_id = torch.from_numpy(ids[:ni].copy()).to(dev)
 d_x = torch.from_numpy(x[:ni].copy()).to(dev)
 d_v = torch.from_numpy(v[:ni].copy()).to(dev)
@@ -43,7 +44,7 @@ if a.accuracy:
     k = 128
     ref = O.force(x[:k], v[:k], m, x, v, 0.0, iid=ids[:k], jid=ids)
 tag = os.path.basename(os.environ.get("G6_B200_LIB", "libsapporo.so"))
-for var in [int(t) for t in a.variants.split(",")]:
+for var, ni in [(int(t), n_) for t in a.variants.split(",") for n_ in nis]:
     for rf in [int(t) for t in a.refine.split(",")]:
         g.set_variant(var)
         L.g6x_set_refine(rf)
@@ -65,6 +66,6 @@ for var in [int(t) for t in a.variants.split(",")]:
             ea = (np.linalg.norm(s[:, 0:3] - ref["acc"], axis=1) / np.linalg.norm(ref["acc"], axis=1)).max()
             ej = (np.linalg.norm(s[:, 3:6] - ref["jerk"], axis=1) / np.linalg.norm(ref["jerk"], axis=1)).max()
             acc = " acc %.2e jerk %.2e" % (ea, ej)
-        print("%-18s variant %d refine %d nn %d: %.3f ms  %.4g int/s  %.1f%% of nominal%s" % (
-            tag, var, rf, a.nn, ms, rate, 100 * rate * 60 / 74.45e12, acc), flush=True)
+        print("%-18s ni %6d variant %d refine %d nn %d: %.3f ms  %.4g int/s  %.1f%% of nominal%s" % (
+            tag, ni, var, rf, a.nn, ms, rate, 100 * rate * 60 / 74.45e12, acc), flush=True)
 g.close()
