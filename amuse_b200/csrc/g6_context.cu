@@ -81,18 +81,19 @@ struct Context {
 
     // staging of j-updates
     std::vector<int> slot_of_addr;  // address -> slot in the pending batch, -1
-    JUpdate *h_up = nullptr;        // pinned
+    JUpdate *h_up = nullptr;        // pinned batch being filled (= h_up2[up_cur])
+    JUpdate *h_up2[2] = {nullptr, nullptr};   // two pinned batches: one fills while the other uploads
+    cudaEvent_t up_done[2] = {nullptr, nullptr};
+    int up_cur = 0;
     JUpdate *d_up = nullptr;
     int up_cap = 0, up_n = 0;
 
     // i-block buffers (npipes)
     float4 *h_i = nullptr;  // pinned [3][npipes]
     float4 *d_i = nullptr;  // [3][npipes]
-    double *d_sum = nullptr;
+    double *d_sum = nullptr;  // [7n doubles][n nearest-neighbour ids] of the current i-block
     u64 *d_key = nullptr;
-    int *d_nnid = nullptr;
-    double *h_sum = nullptr;  // pinned
-    int *h_nnid = nullptr;    // pinned
+    double *h_sum = nullptr;  // pinned, same layout
     // device-resident entry point scratch
     float4 *d_i2 = nullptr;
     int i2_cap = 0;
@@ -104,8 +105,12 @@ struct Context {
     // neighbour lists
     int *d_ngb_cnt = nullptr, *d_ngb_list = nullptr;
     int *h_ngb_cnt = nullptr, *h_ngb_list = nullptr;
-    bool ngb_valid = false;    // lists of the last lasthalf2 are on the device
-    bool ngb_fetched = false;  // ... and on the host
+    bool ngb_valid = false;    // the last lasthalf2 asked for lists (some h2 > 0): they can be built
+    bool ngb_built = false;    // ... have been built on the device
+    bool ngb_fetched = false;  // ... and fetched to the host
+    double *d_sum2 = nullptr;  // scratch outputs of the list-building pass
+    u64 *d_key2 = nullptr;
+    int *d_nnid2 = nullptr;
 
     // captured by firsthalf
     int cur_ni = 0, cur_nj = 0;
@@ -177,12 +182,16 @@ void ensure_up_cap(int need)
 {
     if (need <= G.up_cap) return;
     int newcap = std::max(need, std::max(4096, G.up_cap * 2));
-    JUpdate *nh = nullptr;
-    host_alloc(nh, newcap);
-    if (G.h_up && G.up_n) memcpy(nh, G.h_up, sizeof(JUpdate) * G.up_n);
-    host_free(G.h_up);
-    G.h_up = nh;
-    CK(cudaStreamSynchronize(G.stream));
+    CK(cudaStreamSynchronize(G.stream));   // no upload in flight while the batches move
+    for (int b = 0; b < 2; b++) {
+        JUpdate *nh = nullptr;
+        host_alloc(nh, newcap);
+        if (b == G.up_cur && G.h_up2[b] && G.up_n) memcpy(nh, G.h_up2[b], sizeof(JUpdate) * G.up_n);
+        host_free(G.h_up2[b]);
+        G.h_up2[b] = nh;
+        if (!G.up_done[b]) CK(cudaEventCreateWithFlags(&G.up_done[b], cudaEventDisableTiming));
+    }
+    G.h_up = G.h_up2[G.up_cur];
     dev_free(G.d_up);
     dev_alloc(G.d_up, newcap);
     G.up_cap = newcap;
@@ -196,18 +205,22 @@ void require_open(const char *fn)
     }
 }
 
-// Upload the pending j-updates and scatter them into the state arrays.
+// Upload the pending j-updates and scatter them into the state arrays.  Nothing here waits for the
+// GPU: the next batch is staged in the other pinned buffer (its upload of two flushes ago is long
+// complete; the event wait below is a formality).
 void flush_updates()
 {
     if (G.up_n == 0) return;
     CK(cudaMemcpyAsync(G.d_up, G.h_up, sizeof(JUpdate) * G.up_n, cudaMemcpyHostToDevice, G.stream));
+    CK(cudaEventRecord(G.up_done[G.up_cur], G.stream));
     scatter_kernel<<<(G.up_n + 255) / 256, 256, 0, G.stream>>>(G.up_n, G.d_up, G.js);
     G.launches++;
     CK(cudaGetLastError());
-    // the pinned batch is reused by the next set_j_particle: wait for the copy
-    CK(cudaStreamSynchronize(G.stream));
     for (int k = 0; k < G.up_n; k++) G.slot_of_addr[G.h_up[k].addr] = -1;
     G.up_n = 0;
+    G.up_cur ^= 1;
+    G.h_up = G.h_up2[G.up_cur];
+    CK(cudaEventSynchronize(G.up_done[G.up_cur]));
     G.j_dirty = true;
 }
 
@@ -354,6 +367,9 @@ void launch_force(int nj, int ni, const float4 *iA, const float4 *iB, const floa
     a.tiles_per_split = tps; a.nsplit = nsplit;
     a.ni_pad = ni;
     a.j_offset = G.j_offset;
+    // many splits of few i-blocks: sum the partials with a kernel of its own instead of the last CTA
+    const bool defer = (nsplit > 32) && (n_iblocks * 8 <= slots);
+    a.defer_reduce = defer ? 1 : 0;
     a.eps2 = eps2;
     if (nsplit > 1) ensure_partials((size_t)nsplit * ni);
     a.part_sum = G.part_sum; a.part_key = G.part_key;
@@ -377,23 +393,35 @@ void launch_force(int nj, int ni, const float4 *iA, const float4 *iB, const floa
             exit(-1);
     }
     G.launches++;
+    if (defer) {
+        reduce_partials_kernel<<<(ni * 8 + 255) / 256, 256, 0, G.stream>>>(a, nn ? 1 : 0);
+        CK(cudaGetLastError());
+        G.launches++;
+    }
 }
 
 void free_all()
 {
     for (int k = 0; k < 7; k++) dev_free(G.js.q[k]);
     dev_free(G.js.A); dev_free(G.js.B); dev_free(G.js.C);
-    dev_free(G.d_up); host_free(G.h_up);
+    dev_free(G.d_up);
+    for (int b = 0; b < 2; b++) {
+        host_free(G.h_up2[b]);
+        if (G.up_done[b]) cudaEventDestroy(G.up_done[b]);
+        G.up_done[b] = nullptr;
+    }
+    G.h_up = nullptr; G.up_cur = 0;
     host_free(G.h_i); dev_free(G.d_i); dev_free(G.d_i2);
-    dev_free(G.d_sum); dev_free(G.d_key); dev_free(G.d_nnid);
-    host_free(G.h_sum); host_free(G.h_nnid);
+    dev_free(G.d_sum); dev_free(G.d_key);
+    host_free(G.h_sum);
     dev_free(G.part_sum); dev_free(G.part_key); dev_free(G.tickets);
     dev_free(G.d_ngb_cnt); dev_free(G.d_ngb_list);
+    dev_free(G.d_sum2); dev_free(G.d_key2); dev_free(G.d_nnid2);
     host_free(G.h_ngb_cnt); host_free(G.h_ngb_list);
     G.capacity = 0; G.nj_hi = 0; G.up_cap = 0; G.up_n = 0; G.part_records = 0; G.i2_cap = 0;
     G.slot_of_addr.clear();
     G.predicted_nj = -1; G.j_dirty = false; G.pending = false;
-    G.ngb_valid = G.ngb_fetched = false;
+    G.ngb_valid = G.ngb_built = G.ngb_fetched = false;
 }
 
 void stage_j(int address, int index, double tj, double mass, const double *j6, const double *a2, const double *v,
@@ -496,11 +524,9 @@ int g6_open_(int *id)
     dev_alloc(G.d_i, (size_t)3 * G.npipes);
     dev_alloc(G.d_i2, (size_t)3 * G.npipes);
     G.i2_cap = G.npipes;
-    dev_alloc(G.d_sum, (size_t)7 * G.npipes);
+    dev_alloc(G.d_sum, (size_t)8 * G.npipes);    // [7n doubles][n ints] per i-block
     dev_alloc(G.d_key, (size_t)G.npipes);
-    dev_alloc(G.d_nnid, (size_t)G.npipes);
-    host_alloc(G.h_sum, (size_t)7 * G.npipes);
-    host_alloc(G.h_nnid, (size_t)G.npipes);
+    host_alloc(G.h_sum, (size_t)8 * G.npipes);
     dev_alloc(G.tickets, 65536);
     CK(cudaMemsetAsync(G.tickets, 0, 65536 * sizeof(unsigned int), G.stream));
     G.ti = 0.0;
@@ -564,8 +590,9 @@ void g6calc_firsthalf_(int *cluster_id, int *nj, int *ni, int index[], double xi
     if (G.pending) CK(cudaStreamSynchronize(G.stream));  // a firsthalf without its lasthalf
     flush_updates();
     run_predictor(*nj);
-    // pack the i-block: double -> double-single (sapporo.cpp:125-134)
-    float4 *A = G.h_i, *B = G.h_i + G.npipes, *C = G.h_i + 2 * (size_t)G.npipes;
+    // pack the i-block: double -> double-single (sapporo.cpp:125-134); the three float4 streams are
+    // laid out back to back with stride n, so that they cross PCIe in ONE copy
+    float4 *A = G.h_i, *B = G.h_i + n, *C = G.h_i + 2 * (size_t)n;
     bool any_h2 = false;
     for (int i = 0; i < n; i++) {
         double x = xi[i][0], y = xi[i][1], z = xi[i][2];
@@ -578,17 +605,22 @@ void g6calc_firsthalf_(int *cluster_id, int *nj, int *ni, int index[], double xi
         B[i] = make_float4((float)(x - (double)xh), (float)(y - (double)yh), (float)(z - (double)zh), cv.f);
         C[i] = make_float4((float)vi[i][0], (float)vi[i][1], (float)vi[i][2], 0.f);
     }
-    if (n > 0) {
-        CK(cudaMemcpyAsync(G.d_i, A, sizeof(float4) * n, cudaMemcpyHostToDevice, G.stream));
-        CK(cudaMemcpyAsync(G.d_i + G.npipes, B, sizeof(float4) * n, cudaMemcpyHostToDevice, G.stream));
-        CK(cudaMemcpyAsync(G.d_i + 2 * (size_t)G.npipes, C, sizeof(float4) * n, cudaMemcpyHostToDevice, G.stream));
-    }
+    if (n > 0) CK(cudaMemcpyAsync(G.d_i, G.h_i, sizeof(float4) * 3 * (size_t)n, cudaMemcpyHostToDevice, G.stream));
     G.cur_ni = n;
     G.cur_nj = *nj;
     G.cur_eps2 = (float)*eps2;
     G.cur_any_h2 = any_h2;
     G.pending = true;
     G.ngb_valid = G.ngb_fetched = false;
+    // The force kernel starts here, asynchronously (GRAPE's firsthalf/lasthalf split exists for this
+    // overlap): always with the nearest-neighbour search, which costs ~1 % and is simply not copied
+    // back by g6calc_lasthalf_.  Neighbour-sphere lists are NOT built here: ph4 and phiGRAPE pass
+    // h2 = eps2 on every call (gpu.cc:266,324; gravity.F:72) and never read the lists, so they are
+    // built on demand by g6_read_neighbour_list_.
+    // outputs: [7n doubles][n ints] back to back, so that they come back in ONE copy
+    if (n > 0)
+        launch_force(G.cur_nj, n, G.d_i, G.d_i + n, G.d_i + 2 * (size_t)n, G.cur_eps2, true, false, G.d_sum, G.d_key,
+                     reinterpret_cast<int *>(G.d_sum + 7 * (size_t)n));
 }
 
 static int lasthalf_common(int nj, int ni, double acc[][3], double jerk[][3], double pot[], int *inn)
@@ -601,32 +633,22 @@ static int lasthalf_common(int nj, int ni, double acc[][3], double jerk[][3], do
     }
     (void)nj;
     bool nn = (inn != nullptr);
-    bool list = nn && G.cur_any_h2;
     if (ni > 0) {
-        if (list) {
-            if (!G.d_ngb_cnt) {
-                dev_alloc(G.d_ngb_cnt, (size_t)G.npipes);
-                dev_alloc(G.d_ngb_list, (size_t)G.npipes * G.ngb_cap);
-                host_alloc(G.h_ngb_cnt, (size_t)G.npipes);
-                host_alloc(G.h_ngb_list, (size_t)G.npipes * G.ngb_cap);
-            }
-            CK(cudaMemsetAsync(G.d_ngb_cnt, 0, sizeof(int) * ni, G.stream));
-        }
-        launch_force(G.cur_nj, ni, G.d_i, G.d_i + G.npipes, G.d_i + 2 * (size_t)G.npipes, G.cur_eps2, nn, list,
-                     G.d_sum, G.d_key, G.d_nnid);
-        CK(cudaMemcpyAsync(G.h_sum, G.d_sum, sizeof(double) * 7 * ni, cudaMemcpyDeviceToHost, G.stream));
-        if (nn) CK(cudaMemcpyAsync(G.h_nnid, G.d_nnid, sizeof(int) * ni, cudaMemcpyDeviceToHost, G.stream));
+        const size_t bytes = sizeof(double) * 7 * (size_t)ni + (nn ? sizeof(int) * (size_t)ni : 0);
+        CK(cudaMemcpyAsync(G.h_sum, G.d_sum, bytes, cudaMemcpyDeviceToHost, G.stream));
         CK(cudaStreamSynchronize(G.stream));
+        const int *h_nnid = reinterpret_cast<const int *>(G.h_sum + 7 * (size_t)ni);
         for (int i = 0; i < ni; i++) {
             const double *s = G.h_sum + (size_t)7 * i;
             acc[i][0] = s[0]; acc[i][1] = s[1]; acc[i][2] = s[2];
             jerk[i][0] = s[3]; jerk[i][1] = s[4]; jerk[i][2] = s[5];
             pot[i] = -s[6];
-            if (nn) inn[i] = G.h_nnid[i];
+            if (nn) inn[i] = h_nnid[i];
         }
     }
     G.pending = false;
-    G.ngb_valid = list;
+    G.ngb_valid = nn && G.cur_any_h2 && ni > 0;   // lists of this i-block can be built on demand
+    G.ngb_built = false;
     G.ngb_fetched = false;
     return 0;
 }
@@ -659,6 +681,23 @@ int g6_read_neighbour_list_(int *cluster_id)
         return 0;  // no lists were requested (all h2 <= 0 or lasthalf without nn)
     }
     int ni = G.cur_ni;
+    if (!G.ngb_built) {
+        // second pass over the captured i-block (still in d_i; j state unchanged since its lasthalf2)
+        // with the list-building variant of the masked kernel; forces go to scratch
+        if (!G.d_ngb_cnt) {
+            dev_alloc(G.d_ngb_cnt, (size_t)G.npipes);
+            dev_alloc(G.d_ngb_list, (size_t)G.npipes * G.ngb_cap);
+            host_alloc(G.h_ngb_cnt, (size_t)G.npipes);
+            host_alloc(G.h_ngb_list, (size_t)G.npipes * G.ngb_cap);
+            dev_alloc(G.d_sum2, (size_t)7 * G.npipes);
+            dev_alloc(G.d_key2, (size_t)G.npipes);
+            dev_alloc(G.d_nnid2, (size_t)G.npipes);
+        }
+        CK(cudaMemsetAsync(G.d_ngb_cnt, 0, sizeof(int) * ni, G.stream));
+        launch_force(G.cur_nj, ni, G.d_i, G.d_i + ni, G.d_i + 2 * (size_t)ni, G.cur_eps2, true, true, G.d_sum2,
+                     G.d_key2, G.d_nnid2);
+        G.ngb_built = true;
+    }
     CK(cudaMemcpyAsync(G.h_ngb_cnt, G.d_ngb_cnt, sizeof(int) * ni, cudaMemcpyDeviceToHost, G.stream));
     CK(cudaMemcpyAsync(G.h_ngb_list, G.d_ngb_list, sizeof(int) * (size_t)ni * G.ngb_cap, cudaMemcpyDeviceToHost,
                        G.stream));

@@ -236,6 +236,7 @@ struct ForceArgs {
     int tiles_per_split, nsplit;  // j decomposition over blockIdx.x
     int ni_pad;                   // stride of the partial workspace
     int j_offset;                 // global address of local address 0
+    int defer_reduce;             // 1: stop after the per-split partials (reduce_partials_kernel follows)
     float eps2;
     double *part_sum;             // [nsplit][ni_pad][7]
     u64 *part_key;                // [nsplit][ni_pad]
@@ -402,7 +403,27 @@ __device__ __forceinline__ void reduce_splits(const ForceArgs &p, unsigned int *
         if (i >= p.ni) continue;
         double tot[7] = {0, 0, 0, 0, 0, 0, 0};
         u64 kk = KEY_NONE;
-        for (int sp = 0; sp < p.nsplit; sp++) {
+        // the sums keep their fixed order (split 0, 1, 2, ...: deterministic results); the loads of
+        // eight splits are issued together, since this loop is bound by L2 latency, not bandwidth
+        int sp = 0;
+        for (; sp + 8 <= p.nsplit; sp += 8) {
+            double v[8][7];
+            u64 kv[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                size_t o = (size_t)(sp + u) * p.ni_pad + i;
+#pragma unroll
+                for (int q = 0; q < 7; q++) v[u][q] = __ldcg(p.part_sum + o * 7 + q);
+                kv[u] = __ldcg(p.part_key + o);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+#pragma unroll
+                for (int q = 0; q < 7; q++) tot[q] += v[u][q];
+                kk = kv[u] < kk ? kv[u] : kk;
+            }
+        }
+        for (; sp < p.nsplit; sp++) {
             size_t o = (size_t)sp * p.ni_pad + i;
             const double *r = p.part_sum + o * 7;
 #pragma unroll
@@ -704,8 +725,7 @@ __global__ void __launch_bounds__(THREADS, MINB) force_kernel(const ForceArgs p)
             emit(il, D[k], key[k]);
         }
     }
-    if (single) return;
-
+    if (single || p.defer_reduce) return;
     reduce_splits<NN>(p, &sm.is_last, IB);
 }
 
@@ -1031,8 +1051,44 @@ __global__ void __launch_bounds__(THREADS, MINB) force_fast_kernel(const ForceAr
             p.part_key[o] = key[k];
         }
     }
-    if (single) return;
+    if (single || p.defer_reduce) return;
     reduce_splits<NN>(p, &sm.is_last, IB);
+}
+
+// Sum of the per-split partials as a kernel of its own, for launches with few i-blocks and many
+// j-splits (small i-blocks against many j: the block-timestep regime), where the last CTA of an
+// i-block would sum hundreds of splits alone.  One thread per (i, component); splits are added in
+// order 0,1,2,... like reduce_splits does; 32 loads in flight per thread (L2-latency bound).
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const ForceArgs p, const int want_nn)
+{
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = gid >> 3, q = gid & 7;
+    if (i >= p.ni) return;
+    if (q < 7) {
+        double tot = 0.0;
+        int sp = 0;
+        for (; sp + 32 <= p.nsplit; sp += 32) {
+            double v[32];
+#pragma unroll
+            for (int u = 0; u < 32; u++) v[u] = __ldcg(p.part_sum + ((size_t)(sp + u) * p.ni_pad + i) * 7 + q);
+#pragma unroll
+            for (int u = 0; u < 32; u++) tot += v[u];
+        }
+        for (; sp < p.nsplit; sp++) tot += __ldcg(p.part_sum + ((size_t)sp * p.ni_pad + i) * 7 + q);
+        p.out_sum[(size_t)i * 7 + q] = tot;
+    } else {
+        u64 kk = KEY_NONE;
+        for (int sp = 0; sp < p.nsplit; sp++) {
+            u64 o = __ldcg(p.part_key + (size_t)sp * p.ni_pad + i);
+            kk = o < kk ? o : kk;
+        }
+        p.out_key[i] = kk;
+        if (want_nn) {
+            int id = -1;
+            if (kk != KEY_NONE) id = __float_as_int(p.jB[(int)(unsigned)(kk & 0xffffffffu) - p.j_offset].w);
+            p.out_nnid[i] = id;
+        }
+    }
 }
 
 // After a min-reduction of keys over ranks (each rank holds a j-shard).

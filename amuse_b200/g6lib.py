@@ -149,19 +149,18 @@ class G6:
             n = min(self.npipes, ni - i0)
             cn = C.c_int(n)
             sl = slice(i0, i0 + n)
-            idc, xc, vc, hc = ids[sl].copy(), xi[sl].copy(), vi[sl].copy(), h2[sl].copy()
-            a, j, p = np.empty((n, 3)), np.empty((n, 3)), np.empty(n)
+            # row slices of C-contiguous arrays are contiguous: the library reads the caller's
+            # arrays and writes the results in place, like the C callers do (no staging copies here)
+            idc, xc, vc, hc = ids[sl], xi[sl], vi[sl], h2[sl]
+            a, j, p = acc[sl], jerk[sl], pot[sl]
             self.L.g6calc_firsthalf_(C.byref(self.cid), C.byref(cnj), C.byref(cn), idc, xc, vc, zeros3[:n],
                                      zeros3[:n], zeros1[:n], C.byref(e), hc)
             if want_nn:
-                inn = np.empty(n, dtype=np.int32)
                 self.L.g6calc_lasthalf2_(C.byref(self.cid), C.byref(cnj), C.byref(cn), idc, xc, vc, C.byref(e),
-                                         hc, a, j, p, inn)
-                nn[sl] = inn
+                                         hc, a, j, p, nn[sl])
             else:
                 self.L.g6calc_lasthalf_(C.byref(self.cid), C.byref(cnj), C.byref(cn), idc, xc, vc, C.byref(e),
                                         hc, a, j, p)
-            acc[sl], jerk[sl], pot[sl] = a, j, p
         return dict(acc=acc, jerk=jerk, pot=pot, nn=nn)
 
     def read_neighbour_list(self):
