@@ -116,8 +116,9 @@ def run_reference(a):
         "impl": "reference", "metric": "interactions/s", "value": value, "unit": "interactions/s",
         "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * t_tot / max(1, a.steps),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "full i-block Hermite force sweep, Plummer N=%d, eps2=%g (sampled on CPU)" % (n, a.eps2),
-                   "n": n, "eps2": a.eps2},
+        "config": {"workload": "full i-block Hermite force sweep (acc, jerk, pot, nearest neighbour), "
+                               "Plummer N=%d, eps2=%g; reference CPU loop on a bounded i-sample per step" % (n, a.eps2),
+                   "n": n, "eps2": a.eps2, "sample_i_per_step": ni},
         "cpu_baseline": {"value": value, "unit": "interactions/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "interactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
