@@ -15,6 +15,8 @@
 #include "../../include/g6_b200.h"
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -112,6 +114,24 @@ struct Context {
     u64 *d_key2 = nullptr;
     int *d_nnid2 = nullptr;
 
+    // latency path (small i-blocks): i-block in the kernel parameters, results written by the
+    // kernel into mapped pinned host memory, completion raised as a flag there
+    int direct_max = 2048;             // i-blocks up to this size get their results by direct host writes
+    int inline_max = 384;              // ... and up to this size travel in the kernel parameters
+    int fuse = 1;                      // scatter+predict fused into one launch for small update batches
+    int zc_up_max = 512;               // j-update batches up to this size are read zero-copy by scatter_kernel
+    double *dev_h_sum = nullptr;       // device alias of h_sum
+    JUpdate *dev_h_up2[2] = {nullptr, nullptr};   // device aliases of h_up2[]
+    unsigned long long *h_flag = nullptr, *dev_h_flag = nullptr;
+    unsigned long long flag_seq = 0;
+    unsigned int *d_done = nullptr;
+    bool cur_direct = false;           // the pending i-block signals through h_flag
+    bool i_on_device = false;          // d_i holds the pending/last i-block
+    // G6_B200_TRACE=1: host-side phase timers (seconds), printed by g6_close_
+    int trace = 0;
+    double tr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tr_calls = 0;
+
     // captured by firsthalf
     int cur_ni = 0, cur_nj = 0;
     float cur_eps2 = 0.f;
@@ -142,7 +162,18 @@ void dev_free(T *&p)
 template <typename T>
 void host_alloc(T *&p, size_t n)
 {
-    CK(cudaMallocHost((void **)&p, std::max<size_t>(n, 1) * sizeof(T)));
+    CK(cudaHostAlloc((void **)&p, std::max<size_t>(n, 1) * sizeof(T), cudaHostAllocMapped));
+}
+template <typename T>
+T *dev_alias(T *host_ptr)
+{
+    T *d = nullptr;
+    CK(cudaHostGetDevicePointer((void **)&d, (void *)host_ptr, 0));
+    return d;
+}
+inline double wall()
+{
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 template <typename T>
 void host_free(T *&p)
@@ -189,6 +220,7 @@ void ensure_up_cap(int need)
         if (b == G.up_cur && G.h_up2[b] && G.up_n) memcpy(nh, G.h_up2[b], sizeof(JUpdate) * G.up_n);
         host_free(G.h_up2[b]);
         G.h_up2[b] = nh;
+        G.dev_h_up2[b] = dev_alias(nh);
         if (!G.up_done[b]) CK(cudaEventCreateWithFlags(&G.up_done[b], cudaEventDisableTiming));
     }
     G.h_up = G.h_up2[G.up_cur];
@@ -205,23 +237,68 @@ void require_open(const char *fn)
     }
 }
 
+void run_predictor(int nj);
+
+// The pending batch has been handed to a kernel on the stream: forget it on the host side and switch
+// to the other pinned buffer (its consumer of two flushes ago is long complete; the event wait is a
+// formality).
+void retire_batch()
+{
+    CK(cudaEventRecord(G.up_done[G.up_cur], G.stream));
+    for (int k = 0; k < G.up_n; k++) G.slot_of_addr[G.h_up[k].addr] = -1;
+    G.up_n = 0;
+    G.up_cur ^= 1;
+    G.h_up = G.h_up2[G.up_cur];
+    CK(cudaEventSynchronize(G.up_done[G.up_cur]));
+}
+
 // Upload the pending j-updates and scatter them into the state arrays.  Nothing here waits for the
 // GPU: the next batch is staged in the other pinned buffer (its upload of two flushes ago is long
 // complete; the event wait below is a formality).
 void flush_updates()
 {
     if (G.up_n == 0) return;
-    CK(cudaMemcpyAsync(G.d_up, G.h_up, sizeof(JUpdate) * G.up_n, cudaMemcpyHostToDevice, G.stream));
-    CK(cudaEventRecord(G.up_done[G.up_cur], G.stream));
-    scatter_kernel<<<(G.up_n + 255) / 256, 256, 0, G.stream>>>(G.up_n, G.d_up, G.js);
+    if (G.up_n <= G.zc_up_max) {
+        // small batch (block-timestep regime): the kernel reads the records straight from the mapped
+        // pinned batch over PCIe -- no copy-engine round trip
+        scatter_kernel<<<(G.up_n + 63) / 64, 64, 0, G.stream>>>(G.up_n, G.dev_h_up2[G.up_cur], G.js);
+    } else {
+        CK(cudaMemcpyAsync(G.d_up, G.h_up, sizeof(JUpdate) * G.up_n, cudaMemcpyHostToDevice, G.stream));
+        scatter_kernel<<<(G.up_n + 255) / 256, 256, 0, G.stream>>>(G.up_n, G.d_up, G.js);
+    }
     G.launches++;
     CK(cudaGetLastError());
-    for (int k = 0; k < G.up_n; k++) G.slot_of_addr[G.h_up[k].addr] = -1;
-    G.up_n = 0;
-    G.up_cur ^= 1;
-    G.h_up = G.h_up2[G.up_cur];
-    CK(cudaEventSynchronize(G.up_done[G.up_cur]));
+    retire_batch();
     G.j_dirty = true;
+}
+
+// The batch was consumed by a kernel that scatters AND predicts (update_predict_kernel or a fused
+// single-launch force kernel): same bookkeeping, and the prediction is current afterwards.
+void fill_inline_updates(InlineU &iu)
+{
+    iu.n = G.up_n;
+    for (int k = 0; k < G.up_n; k++) iu.addr[k] = G.h_up[k].addr;
+}
+
+// scatter (if any updates are pending) + predict, in as few launches as possible
+void predict_with_updates(int nj)
+{
+    if (G.up_n == 0 || G.up_n > UPD_MAX || !G.fuse) {
+        flush_updates();
+        run_predictor(nj);
+        return;
+    }
+    if (nj > G.capacity) nj = G.capacity;
+    int n = std::max(nj, std::min(G.nj_hi, G.capacity));
+    InlineU iu;
+    fill_inline_updates(iu);
+    update_predict_kernel<<<(n + 255) / 256, 256, 0, G.stream>>>(n, G.ti, G.js, G.dev_h_up2[G.up_cur], iu);
+    G.launches++;
+    CK(cudaGetLastError());
+    retire_batch();
+    G.predicted_nj = n;
+    G.predicted_ti = G.ti;
+    G.j_dirty = false;
 }
 
 void run_predictor(int nj)
@@ -253,15 +330,16 @@ template <int IPT, int NI_SLOTS, bool PACKED, bool NR, int MINB>
 void launch_variant_nr(const ForceArgs &a, dim3 grid, bool nn, bool list, cudaStream_t st)
 {
     size_t smem = sizeof(ForceSmem);
+    static const InlineI<0> none{};
 #define G6_LAUNCH(NN_, LIST_)                                                                       \
     do {                                                                                            \
-        auto kern = force_kernel<IPT, NI_SLOTS, NN_, LIST_, PACKED, NR, MINB>;                      \
+        auto kern = force_kernel<IPT, NI_SLOTS, NN_, LIST_, PACKED, NR, MINB, 0>;                   \
         static bool attr_set = false;                                                               \
         if (!attr_set) {                                                                            \
             CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
             attr_set = true;                                                                        \
         }                                                                                           \
-        kern<<<grid, THREADS, smem, st>>>(a);                                                       \
+        kern<<<grid, THREADS, smem, st>>>(a, none);                                                 \
     } while (0)
     if (list)
         G6_LAUNCH(true, true);
@@ -280,6 +358,26 @@ void launch_variant(const ForceArgs &a, dim3 grid, bool nn, bool list, cudaStrea
         launch_variant_nr<IPT, NI_SLOTS, PACKED, true, MINB>(a, grid, nn, list, st);
     else
         launch_variant_nr<IPT, NI_SLOTS, PACKED, false, MINB>(a, grid, nn, list, st);
+}
+
+// Latency path: the i-block rides in the kernel parameters (always with the neighbour search, no lists).
+template <int IPT, int NI_SLOTS, bool PACKED, int MINB, int INL>
+void launch_inline(const ForceArgs &a, dim3 grid, const InlineI<INL> &ii, cudaStream_t st)
+{
+    size_t smem = sizeof(ForceSmem);
+#define G6_LAUNCH(NR_)                                                                              \
+    do {                                                                                            \
+        auto kern = force_kernel<IPT, NI_SLOTS, true, false, PACKED, NR_, MINB, INL>;               \
+        static bool attr_set = false;                                                               \
+        if (!attr_set) {                                                                            \
+            CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            attr_set = true;                                                                        \
+        }                                                                                           \
+        kern<<<grid, THREADS, smem, st>>>(a, ii);                                                   \
+    } while (0)
+    if (G.refine) G6_LAUNCH(true); else G6_LAUNCH(false);
+#undef G6_LAUNCH
+    CK(cudaGetLastError());
 }
 
 template <int IPT, int MINB>
@@ -313,21 +411,54 @@ const VariantInfo &variant_info(int v)
     return info[v];
 }
 
-int choose_variant(int ni)
+// Small i-blocks (the block-timestep regime): every thread of a masked kernel walks IB pairs per
+// j-tile (IB = i-particles per CTA), and a launch has ntiles x ceil(ni/IB) CTA-tiles to hand out.  Pick
+// the CTA shape whose modelled makespan -- waves x (tiles per CTA x IB x pair cost + fixed cost), in
+// units of one scalar pair per thread -- is smallest: with few j (small N) the narrow shapes spread
+// the work over more SMs, with many j the wide ones amortise the tile loads.
+int choose_variant(int ni, int nj)
 {
     if (G.variant != V_AUTO) return G.variant;
-    if (ni > 384) return V_F2;
-    if (ni > 48) return V_P2W;
-    if (ni > 4) return V_W1;
-    return V_T1;
+    // the speculative kernel (512 i per CTA, every thread walks every j) needs enough pairs to fill the
+    // chip; below that the narrow masked shapes finish sooner (measured: tools/ + profiles/ latency tables)
+    if (ni > 384 && (double)ni * (double)nj >= 6.0e7) return V_F2;
+    if (ni > 384) return V_P2W;
+    const int cand[3] = {V_T1, V_W1, V_P2W};
+    const double pair_cost[3] = {1.0, 1.0, 0.95};  // measured: in this latency-bound regime packed pairs buy little
+    const double fixed = 64.0;                     // prologue + TMA latency + reduction, in pair units
+    const int ntiles = std::max(1, (nj + TILE - 1) / TILE);
+    int best = V_P2W;
+    double best_cost = 1e300;
+    for (int c = 0; c < 3; c++) {
+        const VariantInfo &vi = variant_info(cand[c]);
+        const int slots = G.sm_count * vi.ctas_per_sm;
+        const int nib = (ni + vi.ib - 1) / vi.ib;
+        const long long cta_tiles = (long long)ntiles * nib;
+        const double waves_min = std::max(1.0, (double)cta_tiles / slots);   // tiles each slot must take
+        const double tps = std::ceil(waves_min);
+        const double cost = tps * vi.ib * pair_cost[c] + fixed * std::max(1.0, (double)nib / slots);
+        if (cost < best_cost) {
+            best_cost = cost;
+            best = cand[c];
+        }
+    }
+    return best;
 }
 
 // Launch the force kernel for i-block (iA,iB,iC) of ni particles against j in [0,nj).
+// inline_src != nullptr: HOST pointer to the packed i-block ([3][ni] float4, stride ni), carried in the
+// kernel parameters (small i-blocks; masked kernels).  flag_seq != 0: outputs are host-mapped and the
+// launch raises G.h_flag = flag_seq when they are complete.
 void launch_force(int nj, int ni, const float4 *iA, const float4 *iB, const float4 *iC, float eps2, bool nn,
-                  bool list, double *out_sum, u64 *out_key, int *out_nnid)
+                  bool list, double *out_sum, u64 *out_key, int *out_nnid, const float4 *inline_src = nullptr,
+                  unsigned long long flag_seq = 0)
 {
     if (nj > G.capacity) nj = G.capacity;
-    int v = choose_variant(ni);
+    int v = choose_variant(ni, nj);
+    if (inline_src && !(v == V_W1 || v == V_T1 || v == V_P2W)) {
+        fprintf(stderr, "g6_b200: FATAL inline i-block with variant %d\n", v);
+        exit(-1);
+    }
     if (list && v == V_F4) v = V_P4;   // neighbour lists test every pair against h2: masked kernels
     if (list && v == V_F2) v = V_P2;
     const VariantInfo &vi = variant_info(v);
@@ -367,8 +498,10 @@ void launch_force(int nj, int ni, const float4 *iA, const float4 *iB, const floa
     a.tiles_per_split = tps; a.nsplit = nsplit;
     a.ni_pad = ni;
     a.j_offset = G.j_offset;
-    // many splits of few i-blocks: sum the partials with a kernel of its own instead of the last CTA
-    const bool defer = (nsplit > 32) && (n_iblocks * 8 <= slots);
+    // many splits of few i-blocks: sum the partials with a kernel of its own (one warp per i, spread
+    // over the SMs) instead of the last CTA -- except for the 4-particle shape, whose last CTA puts
+    // 32 lanes on each i
+    const bool defer = (nsplit > 32) && (n_iblocks * 8 <= slots) && (vi.ib > 4);
     a.defer_reduce = defer ? 1 : 0;
     a.eps2 = eps2;
     if (nsplit > 1) ensure_partials((size_t)nsplit * ni);
@@ -377,6 +510,28 @@ void launch_force(int nj, int ni, const float4 *iA, const float4 *iB, const floa
     a.out_sum = out_sum; a.out_key = out_key; a.out_nnid = out_nnid;
     a.ngb_cnt = G.d_ngb_cnt; a.ngb_list = G.d_ngb_list; a.ngb_cap = G.ngb_cap;
     dim3 grid(nsplit, n_iblocks);
+    const int reduce_ctas = (ni + 7) / 8;   // one warp per i
+    if (flag_seq) {
+        a.done_counter = G.d_done;
+        a.host_flag = G.dev_h_flag;
+        a.flag_seq = flag_seq;
+        a.done_expected = defer ? (unsigned)reduce_ctas : (unsigned)n_iblocks;
+    }
+    if (inline_src) {
+        if (ni <= 64) {
+            InlineI<64> ii;
+            for (int k = 0; k < 3; k++) memcpy(ii.d + 64 * k, inline_src + (size_t)ni * k, sizeof(float4) * ni);
+            if (v == V_T1) launch_inline<1, 4, false, 2, 64>(a, grid, ii, G.stream);
+            else if (v == V_W1) launch_inline<1, 32, false, 2, 64>(a, grid, ii, G.stream);
+            else launch_inline<2, 32, true, 2, 64>(a, grid, ii, G.stream);
+        } else {
+            InlineI<384> ii;
+            for (int k = 0; k < 3; k++) memcpy(ii.d + 384 * k, inline_src + (size_t)ni * k, sizeof(float4) * ni);
+            if (v == V_T1) launch_inline<1, 4, false, 2, 384>(a, grid, ii, G.stream);
+            else if (v == V_W1) launch_inline<1, 32, false, 2, 384>(a, grid, ii, G.stream);
+            else launch_inline<2, 32, true, 2, 384>(a, grid, ii, G.stream);
+        }
+    } else
     switch (v) {
         case V_S4: launch_variant<4, 256, false, 1>(a, grid, nn, list, G.stream); break;
         case V_S2: launch_variant<2, 256, false, 2>(a, grid, nn, list, G.stream); break;
@@ -394,7 +549,7 @@ void launch_force(int nj, int ni, const float4 *iA, const float4 *iB, const floa
     }
     G.launches++;
     if (defer) {
-        reduce_partials_kernel<<<(ni * 8 + 255) / 256, 256, 0, G.stream>>>(a, nn ? 1 : 0);
+        reduce_partials_kernel<<<reduce_ctas, 256, 0, G.stream>>>(a, nn ? 1 : 0);
         CK(cudaGetLastError());
         G.launches++;
     }
@@ -414,6 +569,10 @@ void free_all()
     host_free(G.h_i); dev_free(G.d_i); dev_free(G.d_i2);
     dev_free(G.d_sum); dev_free(G.d_key);
     host_free(G.h_sum);
+    host_free(G.h_flag);
+    dev_free(G.d_done);
+    G.dev_h_sum = nullptr; G.dev_h_flag = nullptr; G.dev_h_up2[0] = G.dev_h_up2[1] = nullptr;
+    G.cur_direct = false; G.i_on_device = false;
     dev_free(G.part_sum); dev_free(G.part_key); dev_free(G.tickets);
     dev_free(G.d_ngb_cnt); dev_free(G.d_ngb_list);
     dev_free(G.d_sum2); dev_free(G.d_key2); dev_free(G.d_nnid2);
@@ -527,6 +686,20 @@ int g6_open_(int *id)
     dev_alloc(G.d_sum, (size_t)8 * G.npipes);    // [7n doubles][n ints] per i-block
     dev_alloc(G.d_key, (size_t)G.npipes);
     host_alloc(G.h_sum, (size_t)8 * G.npipes);
+    G.dev_h_sum = dev_alias(G.h_sum);
+    host_alloc(G.h_flag, 8);
+    G.h_flag[0] = 0;
+    G.dev_h_flag = dev_alias(G.h_flag);
+    G.flag_seq = 0;
+    dev_alloc(G.d_done, 1);
+    CK(cudaMemsetAsync(G.d_done, 0, sizeof(unsigned int), G.stream));
+    G.direct_max = std::min(G.npipes, std::max(0, env_int("G6_B200_DIRECT_MAX", 2048)));
+    G.inline_max = std::min(384, std::max(0, env_int("G6_B200_INLINE_MAX", 384)));
+    G.zc_up_max = std::max(0, env_int("G6_B200_ZC_UPDATES", 512));
+    G.fuse = env_int("G6_B200_FUSE", 1);
+    G.trace = env_int("G6_B200_TRACE", 0);
+    for (double &t : G.tr) t = 0;
+    G.tr_calls = 0;
     dev_alloc(G.tickets, 65536);
     CK(cudaMemsetAsync(G.tickets, 0, 65536 * sizeof(unsigned int), G.stream));
     G.ti = 0.0;
@@ -544,6 +717,13 @@ int g6_close_(int *id)
     if (!G.open) return 0;
     CK(cudaSetDevice(G.device));
     CK(cudaStreamSynchronize(G.stream));
+    if (G.trace && G.tr_calls)
+        fprintf(stderr,
+                "g6_b200 trace: %lld force calls; mean us per call: flush %.2f predict %.2f pack %.2f h2d %.2f "
+                "launch %.2f d2h-issue %.2f wait %.2f unpack %.2f\n",
+                G.tr_calls, 1e6 * G.tr[0] / G.tr_calls, 1e6 * G.tr[1] / G.tr_calls, 1e6 * G.tr[2] / G.tr_calls,
+                1e6 * G.tr[3] / G.tr_calls, 1e6 * G.tr[4] / G.tr_calls, 1e6 * G.tr[5] / G.tr_calls,
+                1e6 * G.tr[6] / G.tr_calls, 1e6 * G.tr[7] / G.tr_calls);
     free_all();
     if (G.own_stream) cudaStreamDestroy(G.own_stream);
     G.own_stream = G.stream = nullptr;
@@ -588,8 +768,18 @@ void g6calc_firsthalf_(int *cluster_id, int *nj, int *ni, int index[], double xi
         exit(-1);
     }
     if (G.pending) CK(cudaStreamSynchronize(G.stream));  // a firsthalf without its lasthalf
-    flush_updates();
-    run_predictor(*nj);
+    double t0 = G.trace ? wall() : 0.0, t1 = 0.0;
+#define G6_TR(k)                      \
+    if (G.trace) {                    \
+        t1 = wall();                  \
+        G.tr[k] += t1 - t0;           \
+        t0 = t1;                      \
+    }
+    // scatter (small batches: fused with the predictor, records read from mapped pinned memory) + predict
+    const bool inl = (n > 0) && (n <= G.inline_max) && (G.variant == V_AUTO);
+    predict_with_updates(*nj);
+    G6_TR(0)
+    G6_TR(1)
     // pack the i-block: double -> double-single (sapporo.cpp:125-134); the three float4 streams are
     // laid out back to back with stride n, so that they cross PCIe in ONE copy
     float4 *A = G.h_i, *B = G.h_i + n, *C = G.h_i + 2 * (size_t)n;
@@ -605,7 +795,14 @@ void g6calc_firsthalf_(int *cluster_id, int *nj, int *ni, int index[], double xi
         B[i] = make_float4((float)(x - (double)xh), (float)(y - (double)yh), (float)(z - (double)zh), cv.f);
         C[i] = make_float4((float)vi[i][0], (float)vi[i][1], (float)vi[i][2], 0.f);
     }
-    if (n > 0) CK(cudaMemcpyAsync(G.d_i, G.h_i, sizeof(float4) * 3 * (size_t)n, cudaMemcpyHostToDevice, G.stream));
+    G6_TR(2)
+    // small i-blocks travel in the kernel parameters (no H2D copy); their results are written by the
+    // kernel into mapped host memory and announced by a flag (no D2H copy, no stream synchronisation)
+    const bool direct = (n > 0) && (n <= G.direct_max);
+    if (n > 0 && !inl) CK(cudaMemcpyAsync(G.d_i, G.h_i, sizeof(float4) * 3 * (size_t)n, cudaMemcpyHostToDevice, G.stream));
+    G.i_on_device = !inl;
+    G.cur_direct = direct;
+    G6_TR(3)
     G.cur_ni = n;
     G.cur_nj = *nj;
     G.cur_eps2 = (float)*eps2;
@@ -618,9 +815,14 @@ void g6calc_firsthalf_(int *cluster_id, int *nj, int *ni, int index[], double xi
     // h2 = eps2 on every call (gpu.cc:266,324; gravity.F:72) and never read the lists, so they are
     // built on demand by g6_read_neighbour_list_.
     // outputs: [7n doubles][n ints] back to back, so that they come back in ONE copy
-    if (n > 0)
-        launch_force(G.cur_nj, n, G.d_i, G.d_i + n, G.d_i + 2 * (size_t)n, G.cur_eps2, true, false, G.d_sum, G.d_key,
-                     reinterpret_cast<int *>(G.d_sum + 7 * (size_t)n));
+    if (n > 0) {
+        double *out = direct ? G.dev_h_sum : G.d_sum;
+        launch_force(G.cur_nj, n, G.d_i, G.d_i + n, G.d_i + 2 * (size_t)n, G.cur_eps2, true, false, out, G.d_key,
+                     reinterpret_cast<int *>(out + 7 * (size_t)n), inl ? G.h_i : nullptr,
+                     direct ? ++G.flag_seq : 0ull);
+    }
+    G6_TR(4)
+    if (G.trace) G.tr_calls++;
 }
 
 static int lasthalf_common(int nj, int ni, double acc[][3], double jerk[][3], double pot[], int *inn)
@@ -634,9 +836,32 @@ static int lasthalf_common(int nj, int ni, double acc[][3], double jerk[][3], do
     (void)nj;
     bool nn = (inn != nullptr);
     if (ni > 0) {
-        const size_t bytes = sizeof(double) * 7 * (size_t)ni + (nn ? sizeof(int) * (size_t)ni : 0);
-        CK(cudaMemcpyAsync(G.h_sum, G.d_sum, bytes, cudaMemcpyDeviceToHost, G.stream));
-        CK(cudaStreamSynchronize(G.stream));
+        double t0 = G.trace ? wall() : 0.0, t1 = 0.0;
+        if (G.cur_direct) {
+            // spin on the flag the kernel raises in mapped host memory
+            volatile unsigned long long *flag = G.h_flag;
+            const unsigned long long want = G.flag_seq;
+            unsigned long long spins = 0;
+            while (*flag != want) {
+                if ((++spins & 0xfffff) == 0) {   // every ~1M polls: is the stream still healthy?
+                    cudaError_t q = cudaStreamQuery(G.stream);
+                    if (q == cudaSuccess) {
+                        if (*flag == want) break;
+                        fprintf(stderr, "g6_b200: FATAL force kernel finished without raising its completion flag\n");
+                        exit(-1);
+                    }
+                    if (q != cudaErrorNotReady) CK(q);
+                }
+            }
+            std::atomic_thread_fence(std::memory_order_acquire);
+            G6_TR(6)
+        } else {
+            const size_t bytes = sizeof(double) * 7 * (size_t)ni + (nn ? sizeof(int) * (size_t)ni : 0);
+            CK(cudaMemcpyAsync(G.h_sum, G.d_sum, bytes, cudaMemcpyDeviceToHost, G.stream));
+            G6_TR(5)
+            CK(cudaStreamSynchronize(G.stream));
+            G6_TR(6)
+        }
         const int *h_nnid = reinterpret_cast<const int *>(G.h_sum + 7 * (size_t)ni);
         for (int i = 0; i < ni; i++) {
             const double *s = G.h_sum + (size_t)7 * i;
@@ -645,6 +870,7 @@ static int lasthalf_common(int nj, int ni, double acc[][3], double jerk[][3], do
             pot[i] = -s[6];
             if (nn) inn[i] = h_nnid[i];
         }
+        G6_TR(7)
     }
     G.pending = false;
     G.ngb_valid = nn && G.cur_any_h2 && ni > 0;   // lists of this i-block can be built on demand
@@ -692,6 +918,10 @@ int g6_read_neighbour_list_(int *cluster_id)
             dev_alloc(G.d_sum2, (size_t)7 * G.npipes);
             dev_alloc(G.d_key2, (size_t)G.npipes);
             dev_alloc(G.d_nnid2, (size_t)G.npipes);
+        }
+        if (!G.i_on_device) {   // the block went out in the kernel parameters: d_i was never written
+            CK(cudaMemcpyAsync(G.d_i, G.h_i, sizeof(float4) * 3 * (size_t)ni, cudaMemcpyHostToDevice, G.stream));
+            G.i_on_device = true;
         }
         CK(cudaMemsetAsync(G.d_ngb_cnt, 0, sizeof(int) * ni, G.stream));
         launch_force(G.cur_nj, ni, G.d_i, G.d_i + ni, G.d_i + 2 * (size_t)ni, G.cur_eps2, true, true, G.d_sum2,

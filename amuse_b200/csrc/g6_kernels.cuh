@@ -65,12 +65,9 @@ __device__ __forceinline__ double pack_mass_id(float m, int id)
     return __hiloint2double(id, __float_as_int(m));
 }
 
-__global__ void scatter_kernel(int n, const JUpdate *__restrict__ up, JState s)
+__device__ __forceinline__ void store_update(const JUpdate &u, const JState &s)
 {
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    JUpdate u = up[k];
-    int a = u.addr;
+    const int a = u.addr;
     s.q[0][a] = make_double2(u.x[0], u.x[1]);
     s.q[1][a] = make_double2(u.x[2], u.t);
     s.q[2][a] = make_double2(u.v[0], u.v[1]);
@@ -79,6 +76,12 @@ __global__ void scatter_kernel(int n, const JUpdate *__restrict__ up, JState s)
     s.q[5][a] = make_double2(u.j[0], u.j[1]);
     s.q[6][a] = make_double2(u.j[2], pack_mass_id(u.m, u.id));
 }
+__global__ void scatter_kernel(int n, const JUpdate *__restrict__ up, JState s)
+{
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    store_update(up[k], s);
+}
 
 // Hermite predictor (jdata.cc:726-747) in FP64, output split to double-single.
 // Algorithmic traffic: 112 B read + 48 B written per j.
@@ -86,10 +89,12 @@ __global__ void scatter_kernel(int n, const JUpdate *__restrict__ up, JState s)
 // records the id range of its massive particles in the spare .w lanes of the tile's first two C
 // entries (C[tile*256].w = min id, C[tile*256+1].w = max id, as int bits): the force kernel uses
 // it to decide per tile whether the self-exclusion masks can be skipped.
-__global__ void __launch_bounds__(TILE) predict_kernel(int n, double ti, JState s)
+// predict_tile: the body, for one tile and the 256 threads of a CTA.  sh_lo/sh_hi: TILE/32 ints of
+// shared memory each.
+__device__ __forceinline__ void predict_tile(const int tile, const int n, const double ti, const JState &s, int *sh_lo,
+                                             int *sh_hi)
 {
-    __shared__ int sh_lo[TILE / 32], sh_hi[TILE / 32];
-    const int j = blockIdx.x * TILE + threadIdx.x;   // always < capacity
+    const int j = tile * TILE + threadIdx.x;   // always < capacity
     const double2 q0 = s.q[0][j], q1 = s.q[1][j], q2 = s.q[2][j], q3 = s.q[3][j], q4 = s.q[4][j], q5 = s.q[5][j],
                   q6 = s.q[6][j];
     const double x = q0.x, y = q0.y, z = q1.x, tj = q1.y, vx = q2.x, vy = q2.y, vz = q3.x;
@@ -134,6 +139,40 @@ __global__ void __launch_bounds__(TILE) predict_kernel(int n, double ti, JState 
     s.A[j] = make_float4(xh, yh, zh, massive ? m : 0.f);
     s.B[j] = make_float4(xl, yl, zl, __int_as_float(id));
     s.C[j] = make_float4((float)qx, (float)qy, (float)qz, cw);
+    __syncthreads();   // sh_lo/sh_hi may be reused by the next tile
+}
+
+// Pending j-updates applied by the kernel that predicts (small batches, block-timestep regime): the
+// addresses ride in the kernel parameters, the 128-byte records are read from mapped pinned host
+// memory by the threads whose address falls into the CTA's j range [j_lo, j_hi).
+constexpr int UPD_MAX = 256;
+struct InlineU {
+    int n;
+    int addr[UPD_MAX];
+};
+__device__ __forceinline__ void apply_updates(const InlineU &iu, const JUpdate *__restrict__ rec, const JState &s,
+                                              const int j_lo, const int j_hi)
+{
+    for (int k = threadIdx.x; k < iu.n; k += blockDim.x) {
+        const int a = iu.addr[k];
+        if (a >= j_lo && a < j_hi) store_update(rec[k], s);
+    }
+    __syncthreads();   // the block's own global writes are visible to its threads after the barrier
+}
+
+__global__ void __launch_bounds__(TILE) predict_kernel(int n, double ti, JState s)
+{
+    __shared__ int sh_lo[TILE / 32], sh_hi[TILE / 32];
+    predict_tile(blockIdx.x, n, ti, s, sh_lo, sh_hi);
+}
+
+// scatter + predict in one launch (small update batches).
+__global__ void __launch_bounds__(TILE) update_predict_kernel(int n, double ti, JState s, const JUpdate *rec,
+                                                              const __grid_constant__ InlineU iu)
+{
+    __shared__ int sh_lo[TILE / 32], sh_hi[TILE / 32];
+    apply_updates(iu, rec, s, blockIdx.x * TILE, (blockIdx.x + 1) * TILE);
+    predict_tile(blockIdx.x, n, ti, s, sh_lo, sh_hi);
 }
 
 // i-block packing for device-resident callers: double -> double-single.
@@ -247,7 +286,40 @@ struct ForceArgs {
     int *ngb_cnt;                 // [ni]   (LIST only; zeroed by the host)
     int *ngb_list;                // [ni][ngb_cap]
     int ngb_cap;
+    // latency path: out_sum/out_nnid point into mapped pinned HOST memory and the CTA that writes the
+    // last outputs raises a flag there, so the host neither issues a D2H copy nor synchronises the stream
+    unsigned int *done_counter;          // device, zero between launches
+    unsigned long long *host_flag;       // mapped pinned host memory (NULL: no signal)
+    unsigned long long flag_seq;         // value to write
+    unsigned int done_expected;          // CTAs that write final outputs in this launch
 };
+
+// i-block carried in the kernel parameters (constant bank) for small i-blocks: no H2D copy at all.
+// Layout [3][N]: iA, iB, iC.  N == 0 is a 48-byte dummy.
+template <int N>
+struct InlineI {
+    float4 d[3 * (N > 0 ? N : 1)];
+};
+
+// Called by ALL threads of a CTA after it has written final outputs.
+__device__ __forceinline__ void signal_done(const ForceArgs &p)
+{
+    if (!p.host_flag) return;
+    __threadfence_system();
+    __syncthreads();
+    if (p.done_expected == 1u) {   // this CTA wrote all outputs: no counting
+        if (threadIdx.x == 0) *reinterpret_cast<volatile unsigned long long *>(p.host_flag) = p.flag_seq;
+        return;
+    }
+    if (threadIdx.x == 0) {
+        const unsigned int k = atomicAdd(p.done_counter, 1u);
+        if (k == p.done_expected - 1u) {
+            *p.done_counter = 0u;   // ready for the next launch (stream order)
+            __threadfence_system();
+            *reinterpret_cast<volatile unsigned long long *>(p.host_flag) = p.flag_seq;
+        }
+    }
+}
 
 struct Acc7 {
     float ax, ay, az, jx, jy, jz, pot;
@@ -383,7 +455,11 @@ __device__ __forceinline__ void interact2(const float4 a, const float4 b, const 
 }
 
 // Split reduction shared by the force kernels: the last CTA of an i-block (ticket) sums the
-// per-split partials in fixed order and writes the outputs.
+// per-split partials and writes the outputs.  Big i-blocks (IB >= THREADS): one thread per i, splits
+// added in order.  Small i-blocks: TPI = min(32, THREADS/IB) lanes share an i, each sums a strided
+// subset of the splits, and a fixed butterfly of shuffles combines them -- the block-timestep regime
+// has hundreds of splits of a handful of i, which one thread per i would walk serially.  Both orders
+// are fixed, so results are deterministic.
 template <bool NN>
 __device__ __forceinline__ void reduce_splits(const ForceArgs &p, unsigned int *is_last, const int IB)
 {
@@ -398,39 +474,7 @@ __device__ __forceinline__ void reduce_splits(const ForceArgs &p, unsigned int *
     __syncthreads();
     if (!*is_last) return;
     __threadfence();
-    for (int il = tid; il < IB; il += THREADS) {
-        int i = blockIdx.y * IB + il;
-        if (i >= p.ni) continue;
-        double tot[7] = {0, 0, 0, 0, 0, 0, 0};
-        u64 kk = KEY_NONE;
-        // the sums keep their fixed order (split 0, 1, 2, ...: deterministic results); the loads of
-        // eight splits are issued together, since this loop is bound by L2 latency, not bandwidth
-        int sp = 0;
-        for (; sp + 8 <= p.nsplit; sp += 8) {
-            double v[8][7];
-            u64 kv[8];
-#pragma unroll
-            for (int u = 0; u < 8; u++) {
-                size_t o = (size_t)(sp + u) * p.ni_pad + i;
-#pragma unroll
-                for (int q = 0; q < 7; q++) v[u][q] = __ldcg(p.part_sum + o * 7 + q);
-                kv[u] = __ldcg(p.part_key + o);
-            }
-#pragma unroll
-            for (int u = 0; u < 8; u++) {
-#pragma unroll
-                for (int q = 0; q < 7; q++) tot[q] += v[u][q];
-                kk = kv[u] < kk ? kv[u] : kk;
-            }
-        }
-        for (; sp < p.nsplit; sp++) {
-            size_t o = (size_t)sp * p.ni_pad + i;
-            const double *r = p.part_sum + o * 7;
-#pragma unroll
-            for (int q = 0; q < 7; q++) tot[q] += __ldcg(r + q);
-            u64 ok = __ldcg(p.part_key + o);
-            kk = ok < kk ? ok : kk;
-        }
+    auto write_out = [&](int i, const double *tot, u64 kk) {
 #pragma unroll
         for (int q = 0; q < 7; q++) p.out_sum[(size_t)i * 7 + q] = tot[q];
         p.out_key[i] = kk;
@@ -439,7 +483,89 @@ __device__ __forceinline__ void reduce_splits(const ForceArgs &p, unsigned int *
             if (kk != KEY_NONE) id = __float_as_int(p.jB[(int)(unsigned)(kk & 0xffffffffu) - p.j_offset].w);
             p.out_nnid[i] = id;
         }
+    };
+    if (IB >= THREADS) {
+        for (int il = tid; il < IB; il += THREADS) {
+            int i = blockIdx.y * IB + il;
+            if (i >= p.ni) continue;
+            double tot[7] = {0, 0, 0, 0, 0, 0, 0};
+            u64 kk = KEY_NONE;
+            // the loads of eight splits are issued together: this loop is bound by L2 latency
+            int sp = 0;
+            for (; sp + 8 <= p.nsplit; sp += 8) {
+                double v[8][7];
+                u64 kv[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    size_t o = (size_t)(sp + u) * p.ni_pad + i;
+#pragma unroll
+                    for (int q = 0; q < 7; q++) v[u][q] = __ldcg(p.part_sum + o * 7 + q);
+                    kv[u] = __ldcg(p.part_key + o);
+                }
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+#pragma unroll
+                    for (int q = 0; q < 7; q++) tot[q] += v[u][q];
+                    kk = kv[u] < kk ? kv[u] : kk;
+                }
+            }
+            for (; sp < p.nsplit; sp++) {
+                size_t o = (size_t)sp * p.ni_pad + i;
+                const double *r = p.part_sum + o * 7;
+#pragma unroll
+                for (int q = 0; q < 7; q++) tot[q] += __ldcg(r + q);
+                u64 ok = __ldcg(p.part_key + o);
+                kk = ok < kk ? ok : kk;
+            }
+            write_out(i, tot, kk);
+        }
+    } else {
+        const int TPI = (THREADS / IB) < 32 ? (THREADS / IB) : 32;   // lanes per i (power of two)
+        const int per_pass = THREADS / TPI;
+        const int sub = tid % TPI;
+        for (int base = 0; base < IB; base += per_pass) {
+            const int il = base + tid / TPI;
+            const int i = blockIdx.y * IB + il;
+            const bool valid = (il < IB) && (i < p.ni);
+            double tot[7] = {0, 0, 0, 0, 0, 0, 0};
+            u64 kk = KEY_NONE;
+            if (valid) {
+                int sp = sub;
+                for (; sp + 3 * TPI < p.nsplit; sp += 4 * TPI) {
+                    double v[4][7];
+                    u64 kv[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        size_t o = (size_t)(sp + u * TPI) * p.ni_pad + i;
+#pragma unroll
+                        for (int q = 0; q < 7; q++) v[u][q] = __ldcg(p.part_sum + o * 7 + q);
+                        kv[u] = __ldcg(p.part_key + o);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+#pragma unroll
+                        for (int q = 0; q < 7; q++) tot[q] += v[u][q];
+                        kk = kv[u] < kk ? kv[u] : kk;
+                    }
+                }
+                for (; sp < p.nsplit; sp += TPI) {
+                    size_t o = (size_t)sp * p.ni_pad + i;
+#pragma unroll
+                    for (int q = 0; q < 7; q++) tot[q] += __ldcg(p.part_sum + o * 7 + q);
+                    u64 ok = __ldcg(p.part_key + o);
+                    kk = ok < kk ? ok : kk;
+                }
+            }
+            for (int off = 1; off < TPI; off <<= 1) {
+#pragma unroll
+                for (int q = 0; q < 7; q++) tot[q] += __shfl_xor_sync(0xffffffffu, tot[q], off);
+                u64 o = __shfl_xor_sync(0xffffffffu, kk, off);
+                kk = o < kk ? o : kk;
+            }
+            if (valid && sub == 0) write_out(i, tot, kk);
+        }
     }
+    signal_done(p);
 }
 
 struct __align__(16) ForceSmem {
@@ -463,8 +589,9 @@ __device__ __forceinline__ u64 make_key(float r2min, int jmin_global)
 // partial sums are flushed to FP64 so that long sums keep ~1e-7 accuracy.
 // Partials of the j-slots are reduced with warp shuffles + shared memory, and the
 // partials of the j-splits by the last CTA to arrive (ticket), in fixed order.
-template <int IPT, int NI_SLOTS, bool NN, bool LIST, bool PACKED, bool NR, int MINB>
-__global__ void __launch_bounds__(THREADS, MINB) force_kernel(const ForceArgs p)
+template <int IPT, int NI_SLOTS, bool NN, bool LIST, bool PACKED, bool NR, int MINB, int INL>
+__global__ void __launch_bounds__(THREADS, MINB) force_kernel(const ForceArgs p,
+                                                              const __grid_constant__ InlineI<INL> ii)
 {
     constexpr int NJ_SLOTS = THREADS / NI_SLOTS;
     constexpr int IB = NI_SLOTS * IPT;
@@ -514,9 +641,15 @@ __global__ void __launch_bounds__(THREADS, MINB) force_kernel(const ForceArgs p)
         float4 a = make_float4(0.f, 0.f, 0.f, -1.f), b = make_float4(0.f, 0.f, 0.f, __int_as_float(0x80000000)),
                c = make_float4(0.f, 0.f, 0.f, 0.f);
         if (i < p.ni) {
-            a = p.iA[i];
-            b = p.iB[i];
-            c = p.iC[i];
+            if (INL > 0) {
+                a = ii.d[i];
+                b = ii.d[INL + i];
+                c = ii.d[2 * INL + i];
+            } else {
+                a = p.iA[i];
+                b = p.iB[i];
+                c = p.iC[i];
+            }
         }
         xh[k] = a.x; yh[k] = a.y; zh[k] = a.z; h2[k] = a.w;
         xl[k] = b.x; yl[k] = b.y; zl[k] = b.z; iid[k] = __float_as_int(b.w);
@@ -725,6 +858,7 @@ __global__ void __launch_bounds__(THREADS, MINB) force_kernel(const ForceArgs p)
             emit(il, D[k], key[k]);
         }
     }
+    if (single) signal_done(p);
     if (single || p.defer_reduce) return;
     reduce_splits<NN>(p, &sm.is_last, IB);
 }
@@ -1051,44 +1185,69 @@ __global__ void __launch_bounds__(THREADS, MINB) force_fast_kernel(const ForceAr
             p.part_key[o] = key[k];
         }
     }
+    if (single) signal_done(p);
     if (single || p.defer_reduce) return;
     reduce_splits<NN>(p, &sm.is_last, IB);
 }
 
-// Sum of the per-split partials as a kernel of its own, for launches with few i-blocks and many
-// j-splits (small i-blocks against many j: the block-timestep regime), where the last CTA of an
-// i-block would sum hundreds of splits alone.  One thread per (i, component); splits are added in
-// order 0,1,2,... like reduce_splits does; 32 loads in flight per thread (L2-latency bound).
+// Sum of the per-split partials as a kernel of its own, for launches of the speculative kernel with
+// few i-blocks and many j-splits, where the last CTA of an i-block would sum hundreds of splits
+// alone.  One warp per i: the lanes take strided subsets of the splits (all loads in flight at once)
+// and a fixed butterfly of shuffles combines them (deterministic).
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const ForceArgs p, const int want_nn)
 {
-    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = gid >> 3, q = gid & 7;
-    if (i >= p.ni) return;
-    if (q < 7) {
-        double tot = 0.0;
-        int sp = 0;
-        for (; sp + 32 <= p.nsplit; sp += 32) {
-            double v[32];
-#pragma unroll
-            for (int u = 0; u < 32; u++) v[u] = __ldcg(p.part_sum + ((size_t)(sp + u) * p.ni_pad + i) * 7 + q);
-#pragma unroll
-            for (int u = 0; u < 32; u++) tot += v[u];
-        }
-        for (; sp < p.nsplit; sp++) tot += __ldcg(p.part_sum + ((size_t)sp * p.ni_pad + i) * 7 + q);
-        p.out_sum[(size_t)i * 7 + q] = tot;
-    } else {
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (i < p.ni) {
+        double tot[7] = {0, 0, 0, 0, 0, 0, 0};
         u64 kk = KEY_NONE;
-        for (int sp = 0; sp < p.nsplit; sp++) {
-            u64 o = __ldcg(p.part_key + (size_t)sp * p.ni_pad + i);
+        int sp = lane;
+        for (; sp + 96 < p.nsplit; sp += 128) {
+            double v[4][7];
+            u64 kv[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                size_t o = (size_t)(sp + 32 * u) * p.ni_pad + i;
+#pragma unroll
+                for (int q = 0; q < 7; q++) v[u][q] = __ldcg(p.part_sum + o * 7 + q);
+                kv[u] = __ldcg(p.part_key + o);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+#pragma unroll
+                for (int q = 0; q < 7; q++) tot[q] += v[u][q];
+                kk = kv[u] < kk ? kv[u] : kk;
+            }
+        }
+        for (; sp < p.nsplit; sp += 32) {
+            size_t o = (size_t)sp * p.ni_pad + i;
+#pragma unroll
+            for (int q = 0; q < 7; q++) tot[q] += __ldcg(p.part_sum + o * 7 + q);
+            u64 ok = __ldcg(p.part_key + o);
+            kk = ok < kk ? ok : kk;
+        }
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+#pragma unroll
+            for (int q = 0; q < 7; q++) tot[q] += __shfl_xor_sync(0xffffffffu, tot[q], off);
+            u64 o = __shfl_xor_sync(0xffffffffu, kk, off);
             kk = o < kk ? o : kk;
         }
-        p.out_key[i] = kk;
-        if (want_nn) {
-            int id = -1;
-            if (kk != KEY_NONE) id = __float_as_int(p.jB[(int)(unsigned)(kk & 0xffffffffu) - p.j_offset].w);
-            p.out_nnid[i] = id;
+        if (lane < 7) {
+            double mine = tot[0];
+#pragma unroll
+            for (int q = 1; q < 7; q++) mine = (lane == q) ? tot[q] : mine;
+            p.out_sum[(size_t)i * 7 + lane] = mine;
+        } else if (lane == 7) {
+            p.out_key[i] = kk;
+            if (want_nn) {
+                int id = -1;
+                if (kk != KEY_NONE) id = __float_as_int(p.jB[(int)(unsigned)(kk & 0xffffffffu) - p.j_offset].w);
+                p.out_nnid[i] = id;
+            }
         }
     }
+    signal_done(p);
 }
 
 // After a min-reduction of keys over ranks (each rank holds a j-shard).

@@ -204,6 +204,37 @@ def test_j_update_visible_and_last_write_wins(g6):
     check_forces(out, ref, what="update")
 
 
+def test_block_step_sequence_across_latency_path_thresholds(g6):
+    """The call pattern of a block time step (gpu.cc:163-230,365-407; gravity.F:54-112, update_grape.F:19-40):
+    ni j-updates, set_ti, firsthalf, lasthalf2 -- with i-block sizes on both sides of every switch of the
+    latency path (i-block in the kernel parameters <= 64 / <= 384, results written straight to host memory
+    <= 2048, scatter fused with the predictor for <= 256 updates) and a moving prediction time."""
+    O = _O()
+    n = 3000
+    m, x, v = P.new_plummer_model(n, seed=11)
+    ids = np.arange(1, n + 1, dtype=np.int32)
+    rnd = np.random.RandomState(5)
+    acc = 0.1 * rnd.standard_normal((n, 3)); jerk = 0.1 * rnd.standard_normal((n, 3))
+    tj = np.zeros(n)
+    _fresh(g6, ids, m, x, v, acc=acc, jerk=jerk, tj=tj)
+    x = x.copy(); v = v.copy()
+    t = 0.0
+    for step, ni in enumerate([1, 4, 5, 32, 33, 64, 65, 255, 256, 257, 384, 385, 1000, 2048, 2049, 3, 3000, 40]):
+        t += 2.0 ** -10
+        sel = np.sort(rnd.choice(n, ni, replace=False))
+        pp, pv = O.predict(t, tj, x, v, acc, jerk)
+        g6.set_ti(t)
+        out = g6.calc(ids[sel], pp[sel], pv[sel], 1e-4)
+        ref = O.force(pp[sel], pv[sel], m, pp, pv, 1e-4, iid=ids[sel], jid=ids, scales=True)
+        check_forces(out, ref, what="block step %d ni %d" % (step, ni))
+        check_nn(out["nn"], ref["nn"], ids, pp[sel], pp)
+        # the caller's corrector stand-in: advance the block to t and send it back (idata::update_gpu)
+        x[sel] = pp[sel]; v[sel] = pv[sel]; tj[sel] = t
+        acc[sel] = out["acc"]; jerk[sel] = out["jerk"]
+        g6.set_j_particles(ids[sel], m[sel], x[sel], v[sel], acc=acc[sel], jerk=jerk[sel], tj=tj[sel],
+                           address=sel.astype(np.int32))
+
+
 def test_neighbour_lists(g6):
     O = _O()
     m, x, v = P.new_plummer_model(3000, seed=8)
