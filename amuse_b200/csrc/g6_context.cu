@@ -132,6 +132,22 @@ struct Context {
     double tr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long tr_calls = 0;
 
+    // multi-GPU exchange over peer memory (g6x_peer_*): see g6_kernels.cuh "Multi-GPU exchange"
+    struct Peer {
+        bool allocated = false, attached = false;
+        int world = 1, rank = 0, cap = 0;
+        unsigned char *buf = nullptr;            // own exchange buffer: [2 halves][world slots] + flags[2][world]
+        unsigned char *peer_buf[MAX_PEERS + 1] = {};   // all ranks' buffers as seen from here ([rank] = buf)
+        size_t slot_bytes = 0, half_bytes = 0, flags_off = 0, buf_bytes = 0;
+        unsigned long long seq = 0;
+        unsigned int *h_err = nullptr, *dev_h_err = nullptr;   // mapped: a combine kernel gave up waiting
+    } peer;
+    // mirrors of the launch being issued (set by g6x_calc_device_allreduce around launch_force)
+    int mir_n = 0;
+    double *mir_sum[MAX_PEERS] = {};
+    u64 *mir_key[MAX_PEERS] = {};
+    int *mir_id[MAX_PEERS] = {};
+
     // captured by firsthalf
     int cur_ni = 0, cur_nj = 0;
     float cur_eps2 = 0.f;
@@ -509,6 +525,12 @@ void launch_force(int nj, int ni, const float4 *iA, const float4 *iB, const floa
     a.tickets = G.tickets;
     a.out_sum = out_sum; a.out_key = out_key; a.out_nnid = out_nnid;
     a.ngb_cnt = G.d_ngb_cnt; a.ngb_list = G.d_ngb_list; a.ngb_cap = G.ngb_cap;
+    a.n_mirror = G.mir_n;
+    for (int m = 0; m < G.mir_n; m++) {
+        a.m_sum[m] = G.mir_sum[m];
+        a.m_key[m] = G.mir_key[m];
+        a.m_id[m] = G.mir_id[m];
+    }
     dim3 grid(nsplit, n_iblocks);
     const int reduce_ctas = (ni + 7) / 8;   // one warp per i
     if (flag_seq) {
@@ -612,20 +634,23 @@ void stage_j(int address, int index, double tj, double mass, const double *j6, c
     if (address + 1 > G.nj_hi) G.nj_hi = address + 1;
 }
 
-// Chunk size of the device path: unlike the ABI path it is not tied to g6_npipes().  For big
-// i-sets pick the chunk whose i-blocks x j-splits fill the resident CTA slots exactly
-// (148 SMs x 2 CTAs = 296 = 37 i-blocks x 8 splits of the speculative kernel), so that no
-// slot idles in a launch; small i-sets go out in one launch.
-int device_chunk(int ni)
+// Chunk size of the device path: unlike the ABI path it is not tied to g6_npipes().  A launch of the
+// speculative kernel should hand out four waves of CTAs (148 SMs x 2 CTAs x 4 = 1184 = i-blocks x
+// j-splits, see launch_force) and give every CTA ~128 j-tiles, so that its prologue, neighbour re-scan
+// and split reduction stay amortised: with all 1M j on one GPU that is 37 i-blocks x 32 splits
+// (18944 i per launch); a rank that holds 1/8 of the j takes 296 i-blocks x 4 splits (151552 i).
+int device_chunk(int ni, int nj)
 {
     int chunk = G.npipes;
     if (G.variant == V_AUTO && ni > G.npipes) {
         const VariantInfo &vi = variant_info(V_F2);
         const int slots = G.sm_count * vi.ctas_per_sm;
-        int split = 1;
-        for (int sdiv = 2; sdiv <= 16; sdiv++)
-            if (slots % sdiv == 0) split = sdiv;
-        chunk = vi.ib * (slots / split);
+        const int ntiles = std::max(1, (nj + TILE - 1) / TILE);
+        int want_split = std::max(1, ntiles / 128);
+        int split = 1;   // largest divisor of 4*slots that does not exceed want_split
+        for (int sdiv = 1; sdiv <= want_split; sdiv++)
+            if ((4 * slots) % sdiv == 0) split = sdiv;
+        chunk = vi.ib * (4 * slots / split);
     }
     return chunk;
 }
@@ -717,6 +742,7 @@ int g6_close_(int *id)
     if (!G.open) return 0;
     CK(cudaSetDevice(G.device));
     CK(cudaStreamSynchronize(G.stream));
+    g6x_peer_detach();
     if (G.trace && G.tr_calls)
         fprintf(stderr,
                 "g6_b200 trace: %lld force calls; mean us per call: flush %.2f predict %.2f pack %.2f h2d %.2f "
@@ -1063,10 +1089,13 @@ int g6x_predict(int nj, double ti)
     return 0;
 }
 
-int g6x_calc_device(int nj, int ni, const int *d_index, const double *d_xi, const double *d_vi, const double *d_h2,
-                    double eps2, int flags, double *d_sum, unsigned long long *d_key, int *d_nnid)
+// Shared body of the device-resident entry points.  With peers attached and `exchange` set, every launch
+// writes this rank's partials into its slot of all exchange buffers (own + peers, over NVLink) and the
+// call ends with the flag + combine kernels, so d_sum/d_key/d_nnid hold the totals over all j-shards.
+static int calc_device_impl(int nj, int ni, const int *d_index, const double *d_xi, const double *d_vi,
+                            const double *d_h2, double eps2, int flags, double *d_sum, unsigned long long *d_key,
+                            int *d_nnid, bool exchange)
 {
-    require_open("g6x_calc_device");
     flush_updates();
     run_predictor(nj);
     bool nn = (flags & 1) != 0, list = (flags & 2) != 0;
@@ -1074,7 +1103,18 @@ int g6x_calc_device(int nj, int ni, const int *d_index, const double *d_xi, cons
         fprintf(stderr, "g6_b200: FATAL g6x_calc_device: neighbour lists are served by the g6 ABI path only\n");
         exit(-1);
     }
-    const int chunk = device_chunk(ni);
+    Context::Peer &P = G.peer;
+    unsigned char *half[MAX_PEERS + 1] = {};
+    if (exchange) {
+        if (!P.attached || ni > P.cap) {
+            fprintf(stderr, "g6_b200: FATAL g6x_calc_device_allreduce: %s (ni %d, capacity %d)\n",
+                    P.attached ? "i-set exceeds the exchange capacity" : "no peers attached", ni, P.cap);
+            exit(-1);
+        }
+        P.seq++;
+        for (int r = 0; r < P.world; r++) half[r] = P.peer_buf[r] + (P.seq & 1) * P.half_bytes + P.rank * P.slot_bytes;
+    }
+    const int chunk = device_chunk(ni, std::min(nj, G.capacity));
     if (chunk > G.i2_cap) {
         CK(cudaStreamSynchronize(G.stream));
         dev_free(G.d_i2);
@@ -1089,15 +1129,137 @@ int g6x_calc_device(int nj, int ni, const int *d_index, const double *d_xi, cons
                                                               C);
         G.launches++;
         CK(cudaGetLastError());
-        launch_force(nj, n, A, B, C, (float)eps2, nn, false, d_sum + 7 * (size_t)i0, d_key + i0, d_nnid + i0);
+        if (!exchange) {
+            launch_force(nj, n, A, B, C, (float)eps2, nn, false, d_sum + 7 * (size_t)i0, d_key + i0, d_nnid + i0);
+            continue;
+        }
+        // slot layout: sum[cap][7] | key[cap] | id[cap]
+        auto s_sum = [&](unsigned char *b) { return reinterpret_cast<double *>(b) + 7 * (size_t)i0; };
+        auto s_key = [&](unsigned char *b) { return reinterpret_cast<u64 *>(b + sizeof(double) * 7 * (size_t)P.cap) + i0; };
+        auto s_id = [&](unsigned char *b) { return reinterpret_cast<int *>(b + sizeof(double) * 8 * (size_t)P.cap) + i0; };
+        G.mir_n = 0;
+        for (int r = 0; r < P.world; r++) {
+            if (r == P.rank) continue;
+            G.mir_sum[G.mir_n] = s_sum(half[r]);
+            G.mir_key[G.mir_n] = s_key(half[r]);
+            G.mir_id[G.mir_n] = s_id(half[r]);
+            G.mir_n++;
+        }
+        launch_force(nj, n, A, B, C, (float)eps2, nn, false, s_sum(half[P.rank]), s_key(half[P.rank]), s_id(half[P.rank]));
+        G.mir_n = 0;
+    }
+    if (exchange && ni > 0) {
+        PeerSlots ps{};
+        ps.world = P.world;
+        ps.rank = P.rank;
+        unsigned char *mine = P.buf + (P.seq & 1) * P.half_bytes;
+        for (int r = 0; r < P.world; r++) {
+            unsigned char *b = mine + r * P.slot_bytes;
+            ps.sum[r] = reinterpret_cast<const double *>(b);
+            ps.key[r] = reinterpret_cast<const u64 *>(b + sizeof(double) * 7 * (size_t)P.cap);
+            ps.id[r] = reinterpret_cast<const int *>(b + sizeof(double) * 8 * (size_t)P.cap);
+        }
+        const size_t foff = P.flags_off + (P.seq & 1) * sizeof(unsigned long long) * P.world;
+        ps.flag = reinterpret_cast<volatile unsigned long long *>(P.buf + foff);
+        ps.n_remote = 0;
+        for (int r = 0; r < P.world; r++)
+            if (r != P.rank)
+                ps.remote_flag[ps.n_remote++] = reinterpret_cast<unsigned long long *>(P.peer_buf[r] + foff) + P.rank;
+        peer_flag_kernel<<<1, 32, 0, G.stream>>>(ps, P.seq);
+        CK(cudaGetLastError());
+        const int ctas = std::max(1, std::min(2 * G.sm_count, (ni + 255) / 256));
+        peer_combine_kernel<<<ctas, 256, 0, G.stream>>>(ps, P.seq, ni, d_sum, d_key, d_nnid, P.dev_h_err);
+        CK(cudaGetLastError());
+        G.launches += 2;
     }
     return 0;
+}
+
+int g6x_calc_device(int nj, int ni, const int *d_index, const double *d_xi, const double *d_vi, const double *d_h2,
+                    double eps2, int flags, double *d_sum, unsigned long long *d_key, int *d_nnid)
+{
+    require_open("g6x_calc_device");
+    return calc_device_impl(nj, ni, d_index, d_xi, d_vi, d_h2, eps2, flags, d_sum, d_key, d_nnid, false);
+}
+
+int g6x_calc_device_allreduce(int nj, int ni, const int *d_index, const double *d_xi, const double *d_vi,
+                              const double *d_h2, double eps2, int flags, double *d_sum, unsigned long long *d_key,
+                              int *d_nnid)
+{
+    require_open("g6x_calc_device_allreduce");
+    return calc_device_impl(nj, ni, d_index, d_xi, d_vi, d_h2, eps2, flags, d_sum, d_key, d_nnid, true);
+}
+
+int g6x_peer_handle_bytes(void) { return (int)sizeof(cudaIpcMemHandle_t); }
+
+int g6x_peer_alloc(int world, int rank, int capacity, void *handle_out)
+{
+    require_open("g6x_peer_alloc");
+    Context::Peer &P = G.peer;
+    if (world < 1 || world > MAX_PEERS + 1 || rank < 0 || rank >= world || capacity <= 0) return -1;
+    if (P.allocated) g6x_peer_detach();
+    P.world = world;
+    P.rank = rank;
+    P.cap = (capacity + 15) / 16 * 16;
+    P.slot_bytes = (size_t)P.cap * (sizeof(double) * 7 + sizeof(u64) + sizeof(int));
+    P.half_bytes = P.slot_bytes * world;
+    P.flags_off = 2 * P.half_bytes;
+    P.buf_bytes = P.flags_off + 2 * sizeof(unsigned long long) * world;
+    CK(cudaMalloc((void **)&P.buf, P.buf_bytes));
+    CK(cudaMemset(P.buf, 0, P.buf_bytes));
+    host_alloc(P.h_err, 1);
+    P.h_err[0] = 0;
+    P.dev_h_err = dev_alias(P.h_err);
+    P.seq = 0;
+    P.allocated = true;
+    P.attached = false;
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, P.buf));
+    memcpy(handle_out, &h, sizeof(h));
+    return 0;
+}
+
+int g6x_peer_attach(const void *handles)
+{
+    require_open("g6x_peer_attach");
+    Context::Peer &P = G.peer;
+    if (!P.allocated) return -1;
+    const cudaIpcMemHandle_t *h = static_cast<const cudaIpcMemHandle_t *>(handles);
+    for (int r = 0; r < P.world; r++) {
+        if (r == P.rank) {
+            P.peer_buf[r] = P.buf;
+            continue;
+        }
+        void *q = nullptr;
+        CK(cudaIpcOpenMemHandle(&q, h[r], cudaIpcMemLazyEnablePeerAccess));
+        P.peer_buf[r] = static_cast<unsigned char *>(q);
+    }
+    P.attached = true;
+    return 0;
+}
+
+int g6x_peer_detach(void)
+{
+    Context::Peer &P = G.peer;
+    if (!P.allocated) return 0;
+    if (G.open) CK(cudaStreamSynchronize(G.stream));
+    for (int r = 0; r < P.world; r++)
+        if (P.attached && r != P.rank && P.peer_buf[r]) cudaIpcCloseMemHandle(P.peer_buf[r]);
+    if (P.buf) cudaFree(P.buf);
+    host_free(P.h_err);
+    P = Context::Peer{};
+    return 0;
+}
+
+int g6x_peer_error(void)
+{
+    return (G.peer.allocated && G.peer.h_err) ? (int)G.peer.h_err[0] : 0;
 }
 
 int g6x_device_chunk(int ni)
 {
     require_open("g6x_device_chunk");
-    return device_chunk(ni);
+    return device_chunk(ni, std::min(G.nj_hi, G.capacity));
 }
 
 int g6x_resolve_nn(int ni, const unsigned long long *d_key, int rank, int *d_nnid)

@@ -268,6 +268,7 @@ __device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c)
 // ---------------------------------------------------------------------------
 // Force kernel.
 // ---------------------------------------------------------------------------
+constexpr int MAX_PEERS = 7;   // other ranks of one NVSwitch domain (8 GPUs)
 struct ForceArgs {
     const float4 *jA, *jB, *jC;   // predicted j (device)
     const float4 *iA, *iB, *iC;   // packed i-block (device)
@@ -292,6 +293,13 @@ struct ForceArgs {
     unsigned long long *host_flag;       // mapped pinned host memory (NULL: no signal)
     unsigned long long flag_seq;         // value to write
     unsigned int done_expected;          // CTAs that write final outputs in this launch
+    // multi-GPU exchange fused into the force kernel: whoever writes final outputs of this rank's
+    // j-shard also stores them into its slot of every peer's exchange buffer over NVLink (peer pointers
+    // from CUDA IPC), so the partials travel while the other i-blocks are still being computed
+    int n_mirror;
+    double *m_sum[MAX_PEERS];            // [ni][7] at each peer, already offset to this launch's first i
+    u64 *m_key[MAX_PEERS];
+    int *m_id[MAX_PEERS];
 };
 
 // i-block carried in the kernel parameters (constant bank) for small i-blocks: no H2D copy at all.
@@ -300,6 +308,24 @@ template <int N>
 struct InlineI {
     float4 d[3 * (N > 0 ? N : 1)];
 };
+
+// Final outputs of particle i (local arrays + the peers' exchange slots).
+template <bool NN>
+__device__ __forceinline__ void store_outputs(const ForceArgs &p, const int i, const double *tot, const u64 kk)
+{
+    int id = -1;
+    if (NN && kk != KEY_NONE) id = __float_as_int(p.jB[(int)(unsigned)(kk & 0xffffffffu) - p.j_offset].w);
+#pragma unroll
+    for (int q = 0; q < 7; q++) p.out_sum[(size_t)i * 7 + q] = tot[q];
+    p.out_key[i] = kk;
+    if (NN) p.out_nnid[i] = id;
+    for (int m = 0; m < p.n_mirror; m++) {
+#pragma unroll
+        for (int q = 0; q < 7; q++) p.m_sum[m][(size_t)i * 7 + q] = tot[q];
+        p.m_key[m][i] = kk;
+        p.m_id[m][i] = id;
+    }
+}
 
 // Called by ALL threads of a CTA after it has written final outputs.
 __device__ __forceinline__ void signal_done(const ForceArgs &p)
@@ -474,16 +500,7 @@ __device__ __forceinline__ void reduce_splits(const ForceArgs &p, unsigned int *
     __syncthreads();
     if (!*is_last) return;
     __threadfence();
-    auto write_out = [&](int i, const double *tot, u64 kk) {
-#pragma unroll
-        for (int q = 0; q < 7; q++) p.out_sum[(size_t)i * 7 + q] = tot[q];
-        p.out_key[i] = kk;
-        if (NN) {
-            int id = -1;
-            if (kk != KEY_NONE) id = __float_as_int(p.jB[(int)(unsigned)(kk & 0xffffffffu) - p.j_offset].w);
-            p.out_nnid[i] = id;
-        }
-    };
+    auto write_out = [&](int i, const double *tot, u64 kk) { store_outputs<NN>(p, i, tot, kk); };
     if (IB >= THREADS) {
         for (int il = tid; il < IB; il += THREADS) {
             int i = blockIdx.y * IB + il;
@@ -823,14 +840,7 @@ __global__ void __launch_bounds__(THREADS, MINB) force_kernel(const ForceArgs p,
         int i = blockIdx.y * IB + il;
         if (i >= p.ni) return;
         if (single) {
-#pragma unroll
-            for (int q = 0; q < 7; q++) p.out_sum[(size_t)i * 7 + q] = tot[q];
-            p.out_key[i] = kk;
-            if (NN) {
-                int id = -1;
-                if (kk != KEY_NONE) id = __float_as_int(p.jB[(int)(unsigned)(kk & 0xffffffffu) - p.j_offset].w);
-                p.out_nnid[i] = id;
-            }
+            store_outputs<NN>(p, i, tot, kk);
         } else {
             size_t o = (size_t)blockIdx.x * p.ni_pad + i;
 #pragma unroll
@@ -1170,14 +1180,7 @@ __global__ void __launch_bounds__(THREADS, MINB) force_fast_kernel(const ForceAr
         const int i = i_of(k);
         if (i >= p.ni) continue;
         if (single) {
-#pragma unroll
-            for (int q = 0; q < 7; q++) p.out_sum[(size_t)i * 7 + q] = D[k][q];
-            p.out_key[i] = key[k];
-            if (NN) {
-                int id = -1;
-                if (key[k] != KEY_NONE) id = __float_as_int(p.jB[(int)(unsigned)(key[k] & 0xffffffffu) - p.j_offset].w);
-                p.out_nnid[i] = id;
-            }
+            store_outputs<NN>(p, i, D[k], key[k]);
         } else {
             size_t o = (size_t)blockIdx.x * p.ni_pad + i;
 #pragma unroll
@@ -1233,18 +1236,9 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const ForceArgs p,
             u64 o = __shfl_xor_sync(0xffffffffu, kk, off);
             kk = o < kk ? o : kk;
         }
-        if (lane < 7) {
-            double mine = tot[0];
-#pragma unroll
-            for (int q = 1; q < 7; q++) mine = (lane == q) ? tot[q] : mine;
-            p.out_sum[(size_t)i * 7 + lane] = mine;
-        } else if (lane == 7) {
-            p.out_key[i] = kk;
-            if (want_nn) {
-                int id = -1;
-                if (kk != KEY_NONE) id = __float_as_int(p.jB[(int)(unsigned)(kk & 0xffffffffu) - p.j_offset].w);
-                p.out_nnid[i] = id;
-            }
+        if (lane == 0) {
+            if (want_nn) store_outputs<true>(p, i, tot, kk);
+            else store_outputs<false>(p, i, tot, kk);
         }
     }
     signal_done(p);
@@ -1265,6 +1259,81 @@ __global__ void resolve_nn_kernel(int ni, const u64 *__restrict__ key, int rank,
         if (a >= 0 && a < nj_local) id = __float_as_int(jB[a].w);
     }
     nnid[i] = id;
+}
+
+// ---------------------------------------------------------------------------
+// Multi-GPU exchange (one process per GPU, peer memory over NVLink/NVSwitch).
+//
+// Every rank owns an exchange buffer with one slot per rank: slot[r] = { sum[cap][7], key[cap],
+// id[cap] } holds rank r's partial results (written by r's force kernels, see store_outputs) and
+// flag[r] the sequence number of the last exchange r has completed into this buffer.  After its last
+// force launch of an exchange, rank r runs peer_flag_kernel (remote stores of seq into flag[r] at every
+// peer); peer_combine_kernel then waits for all flags of the LOCAL buffer and combines the slots in
+// rank order -- the device-side form of idata.cc:284-313 (sum pot/acc/jerk, min dnn, nn of the winner),
+// identical on every rank.
+// ---------------------------------------------------------------------------
+struct PeerSlots {
+    int world, rank;
+    const double *sum[MAX_PEERS + 1];   // local buffer, slot r: [cap][7]
+    const u64 *key[MAX_PEERS + 1];
+    const int *id[MAX_PEERS + 1];
+    volatile unsigned long long *flag;  // local buffer: [world]
+    unsigned long long *remote_flag[MAX_PEERS];   // &flag[rank] at every peer
+    int n_remote;
+};
+
+__global__ void peer_flag_kernel(const PeerSlots ps, const unsigned long long seq)
+{
+    // the force kernels that wrote into the peers' slots precede this kernel on the stream
+    __threadfence_system();
+    if (threadIdx.x < ps.n_remote) {
+        *reinterpret_cast<volatile unsigned long long *>(ps.remote_flag[threadIdx.x]) = seq;
+    }
+    if (threadIdx.x == 0) ps.flag[ps.rank] = seq;
+}
+
+// grid <= resident CTAs (the host sizes it): every CTA waits, then takes a grid-stride share of i
+__global__ void __launch_bounds__(256) peer_combine_kernel(const PeerSlots ps, const unsigned long long seq, const int ni,
+                                                          double *out_sum, u64 *out_key, int *out_nnid,
+                                                          unsigned int *error_word)
+{
+    __shared__ int ok;
+    if (threadIdx.x == 0) {
+        ok = 1;
+        for (int r = 0; r < ps.world; r++) {
+            unsigned long long spins = 0;
+            while (ps.flag[r] < seq) {
+                __nanosleep(200);
+                if (++spins > (1ull << 26)) {   // ~15 s: a peer died; report instead of hanging the GPU
+                    ok = 0;
+                    atomicExch(error_word, 1u);
+                    break;
+                }
+            }
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+    if (!ok) return;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ni; i += gridDim.x * blockDim.x) {
+        double tot[7] = {0, 0, 0, 0, 0, 0, 0};
+        u64 kk = KEY_NONE;
+        int id = -1;
+        for (int r = 0; r < ps.world; r++) {
+            const double *s = ps.sum[r] + (size_t)i * 7;
+#pragma unroll
+            for (int q = 0; q < 7; q++) tot[q] += __ldcv(s + q);
+            const u64 k = __ldcv(ps.key[r] + i);
+            if (k < kk) {   // strict: the lowest rank wins exact ties, like the ascending-j CPU scan
+                kk = k;
+                id = __ldcv(ps.id[r] + i);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 7; q++) out_sum[(size_t)i * 7 + q] = tot[q];
+        out_key[i] = kk;
+        out_nnid[i] = id;
+    }
 }
 
 // ---------------------------------------------------------------------------

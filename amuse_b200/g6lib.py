@@ -29,6 +29,8 @@ G6_SYMBOLS = [
     "g6x_version", "g6x_set_stream", "g6x_set_refine", "g6x_set_j_offset", "g6x_set_j_particles", "g6x_predict",
     "g6x_calc_device", "g6x_device_chunk", "g6x_resolve_nn", "g6x_synchronize", "g6x_launch_count", "g6x_get_predicted",
     "g6x_read_predicted", "g6x_time_predictor", "g6x_set_variant", "g6x_fp32_peak",
+    "g6x_peer_handle_bytes", "g6x_peer_alloc", "g6x_peer_attach", "g6x_peer_detach", "g6x_peer_error",
+    "g6x_calc_device_allreduce",
 ]
 
 _dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
@@ -67,6 +69,9 @@ def load():
     L.g6x_predict.argtypes = [C.c_int, C.c_double]
     L.g6x_calc_device.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.g6x_calc_device_allreduce.argtypes = L.g6x_calc_device.argtypes
+    L.g6x_peer_alloc.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p]
+    L.g6x_peer_attach.argtypes = [C.c_void_p]
     L.g6x_device_chunk.argtypes = [C.c_int]
     L.g6x_resolve_nn.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p]
     L.g6x_launch_count.restype = C.c_longlong

@@ -13,6 +13,12 @@ whole i-block against it, and the partials are combined like the tail of
 The functions take torch tensors on any device and use whatever process group is active
 (NCCL over NVLink on the B200 box, gloo in the CPU tests).  No arithmetic of the force path
 lives here.
+
+On the GPU box the same combination is also available INSIDE the library (``attach_peers`` +
+``g6x_calc_device_allreduce``): the force kernels store their partials straight into the peers'
+exchange buffers over NVLink (CUDA IPC peer memory) while other i-blocks are still being computed,
+and one combine kernel per call replaces the three collectives.  ``combine_partials`` (NCCL) stays
+as the reference implementation the fused path is tested against.
 """
 KEY_NONE = 0x7F800000FFFFFFFF
 
@@ -50,3 +56,26 @@ def combine_partials(d_sum, d_key, resolve_ids, group=None):
     d_nn = resolve_ids(d_key)
     dist.all_reduce(d_nn, op=dist.ReduceOp.SUM, group=group)
     return d_nn
+
+
+def attach_peers(lib, capacity, group=None):
+    """Set up the library's peer-memory exchange for i-sets of up to `capacity` particles:
+    g6x_peer_alloc on every rank, all-gather of the CUDA IPC handles over the process group,
+    g6x_peer_attach.  `lib` is the ctypes handle of the opened library (G6.L).  Returns world size."""
+    import ctypes as C
+
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    nbytes = lib.g6x_peer_handle_bytes()
+    mine = C.create_string_buffer(nbytes)
+    if lib.g6x_peer_alloc(world, rank, int(capacity), mine) != 0:
+        raise RuntimeError("g6x_peer_alloc failed (world %d, capacity %d)" % (world, capacity))
+    handles = [None] * world
+    dist.all_gather_object(handles, bytes(mine.raw), group=group)
+    blob = C.create_string_buffer(b"".join(handles), nbytes * world)
+    if lib.g6x_peer_attach(blob) != 0:
+        raise RuntimeError("g6x_peer_attach failed")
+    dist.barrier(group=group)
+    return world

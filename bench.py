@@ -44,13 +44,18 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=1 << 20, help="particles (default 1M, the headline size)")
+    ap.add_argument("--n", "--particles", dest="n", type=int, default=1 << 20,
+                    help="particles (default 1M, the headline size); spell it --particles under torchrun, whose "
+                         "own parser treats --n as an abbreviation")
     ap.add_argument("--eps2", type=float, default=0.0)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N>1: combine the j-shard partials inside the library over peer memory (default) or with "
+                         "three NCCL all-reduces (the reference implementation of the exchange)")
     return ap.parse_args()
 
 
@@ -207,6 +212,8 @@ def run_b200(a):
         g.set_variant(a.variant)
     g.set_j_particles(ids[j0:j1], mass[j0:j1], pos[j0:j1], vel[j0:j1])
     njl = j1 - j0
+    if world > 1 and a.exchange == "peer":
+        S.attach_peers(L, n)      # CUDA IPC handles gathered over the process group
     npipes = g.npipes
     dchunk = L.g6x_device_chunk(n)           # i-particles per force-kernel launch on the device path
     n_launch = (n + dchunk - 1) // dchunk
@@ -236,12 +243,15 @@ def run_b200(a):
             e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
             e0.record()
         # one call for the whole i-set: the library cuts it into launches of `dchunk` i-particles
-        L.g6x_calc_device(njl, n, d_id.data_ptr(), d_x.data_ptr(), d_v.data_ptr(), None, a.eps2, 1,
-                          d_sum.data_ptr(), d_key.data_ptr(), d_nn.data_ptr())
+        # idata.cc:284-313 on the device (sum, min key, id of the winner): either fused into the force
+        # kernels (stores into the peers' exchange buffers over NVLink + one combine kernel) ...
+        calc = L.g6x_calc_device_allreduce if (world > 1 and a.exchange == "peer") else L.g6x_calc_device
+        calc(njl, n, d_id.data_ptr(), d_x.data_ptr(), d_v.data_ptr(), None, a.eps2, 1,
+             d_sum.data_ptr(), d_key.data_ptr(), d_nn.data_ptr())
         if record:
             e1.record()
             chunk_events.append((e0, e1, n))
-        if world > 1:      # idata.cc:284-313 on the device: sum, min-key, owner-resolved id
+        if world > 1 and a.exchange == "nccl":      # ... or as three NCCL all-reduces
             S.combine_partials(d_sum, d_key, resolve)
 
     def barrier():
@@ -270,6 +280,8 @@ def run_b200(a):
     barrier()
     t_wall1 = time.perf_counter()
     launches = g.launch_count() - launches0
+    if world > 1 and a.exchange == "peer" and L.g6x_peer_error():
+        raise SystemExit("bench.py: a combine kernel gave up waiting for a peer (g6x_peer_error)")
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
     ms_local = sum(e0.elapsed_time(e1) for e0, e1 in ev)
     ms_t = torch.tensor([ms_local], dtype=torch.float64, device=dev)
@@ -329,7 +341,8 @@ def run_b200(a):
             dist.all_reduce(dt_t, op=dist.ReduceOp.MAX)
             dt = float(dt_t.item())
             h2d, d2h = (4 + 48) * n, 60 * n
-            how = "pinned host i-arrays -> H2D -> g6x_calc_device -> NCCL all-reduce -> D2H, per rank"
+            how = "pinned host i-arrays -> H2D -> g6x_calc_device%s -> D2H, per rank" % (
+                "_allreduce (peer-memory exchange)" if a.exchange == "peer" else " -> 3 NCCL all-reduces")
         e2e = {"value": float(n) * float(n) / dt, "unit": "interactions/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": dt * 1e3, "how": how}
 
@@ -358,7 +371,9 @@ def run_b200(a):
                                    "Plummer N=%d, eps2=%g, %d i-particles per launch, j sharded over %d GPU(s)" % (
                                        n, a.eps2, dchunk, world),
                        "n": n, "eps2": a.eps2, "npipes": npipes, "i_per_launch": dchunk, "l2": "256 MiB buffer written between timed steps",
-                       "parallelism": "j-shard x%d + all-reduce" % world},
+                       "parallelism": "j-shard x%d + %s" % (world, "none" if world == 1 else (
+                           "peer-memory exchange fused into the force kernels (NVLink stores + combine kernel)"
+                           if a.exchange == "peer" else "3 NCCL all-reduces"))},
             "tflops_60": value * FLOP_PER_INTERACTION / 1e12,
             "frac_fp32_peak_nominal": value * FLOP_PER_INTERACTION / 1e12 / (NOMINAL_FP32_TFLOPS * world),
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": NOMINAL_FP32_TFLOPS, "unit": "TFLOP/s",

@@ -165,9 +165,31 @@ int g6x_calc_device(int nj, int ni, const int *d_index, const double *d_xi,
                     const double *d_vi, const double *d_h2, double eps2,
                     int flags, double *d_sum, unsigned long long *d_key,
                     int *d_nnid);
-/* i-particles per kernel launch that g6x_calc_device uses for an i-set of ni (it
- * picks the chunk whose i-blocks x j-splits fill the resident CTA slots exactly;
- * g6_npipes_() only bounds the ABI path). */
+/* ---- multi-GPU exchange over peer memory (one process per GPU, NVLink/NVSwitch) ----
+ * Replaces the five host MPI_Allreduce of idata::get_acc_and_jerk (idata.cc:284-313) by stores into
+ * the peers' memory issued from inside the force kernels plus one combine kernel.
+ *   1. every rank: g6x_peer_alloc(world, rank, capacity, handle) -- allocates its exchange buffer for
+ *      i-sets of up to `capacity` particles and returns an opaque handle (g6x_peer_handle_bytes() bytes,
+ *      a CUDA IPC memory handle);
+ *   2. the caller gathers the handles of all ranks (any transport: torch.distributed, MPI, a file);
+ *   3. every rank: g6x_peer_attach(handles[world]) -- maps the peers' buffers;
+ *   4. g6x_calc_device_allreduce(...) -- as g6x_calc_device, but every rank's d_sum/d_key/d_nnid
+ *      receive the combination over all j-shards (sum, min key, id of the winner).  Collective: all
+ *      ranks must call it in the same order.  g6x_set_j_offset() gives the keys their global address.
+ * g6x_peer_error() != 0 after a synchronize means a combine kernel gave up waiting for a peer. */
+int g6x_peer_handle_bytes(void);
+int g6x_peer_alloc(int world, int rank, int capacity, void *handle_out);
+int g6x_peer_attach(const void *handles);
+int g6x_peer_detach(void);
+int g6x_peer_error(void);
+int g6x_calc_device_allreduce(int nj, int ni, const int *d_index,
+                              const double *d_xi, const double *d_vi,
+                              const double *d_h2, double eps2, int flags,
+                              double *d_sum, unsigned long long *d_key,
+                              int *d_nnid);
+/* i-particles per kernel launch that g6x_calc_device uses for an i-set of ni against
+ * the j currently loaded (it picks the chunk whose i-blocks x j-splits make four full
+ * waves of CTAs with ~128 j-tiles each; g6_npipes_() only bounds the ABI path). */
 int g6x_device_chunk(int ni);
 /* After a min-reduction of d_key over ranks: d_nnid[i] = id of the winning j if
  * this rank owns it, else 0 (so a sum over ranks gives the id), -1 on rank 0

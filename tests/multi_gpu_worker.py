@@ -1,0 +1,104 @@
+"""Worker of tests/test_gpu_multi.py, one rank per GPU (torchrun): j sharded over the ranks like
+jdata::define_domain (jdata.cc:56-67); the partial forces are combined (a) by the NCCL collectives of
+amuse_b200/sharding.py and (b) inside the library over peer memory (g6x_calc_device_allreduce), and both
+are checked against the FP64 oracle on rank 0.  Prints one line 'MULTI-GPU OK ...' on success."""
+import ctypes as C
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from amuse_b200 import g6lib, plummer as P, sharding as S  # noqa: E402
+
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
+    world = int(os.environ["WORLD_SIZE"]); rank = int(os.environ["RANK"]); local = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    m, x, v = P.new_plummer_model(n, seed=4)
+    ids = np.arange(1, n + 1, dtype=np.int32)
+    j0, j1 = S.define_domain(n, world, rank)
+    g = g6lib.G6(local)
+    L = g.L
+    L.g6x_set_stream(C.c_void_p(torch.cuda.current_stream(dev).cuda_stream), 1)
+    L.g6x_set_j_offset(j0)
+    g.set_j_particles(ids[j0:j1], m[j0:j1], x[j0:j1], v[j0:j1])
+    njl = j1 - j0
+    S.attach_peers(L, n)
+
+    d_id = torch.from_numpy(ids).to(dev); d_x = torch.from_numpy(x).to(dev); d_v = torch.from_numpy(v).to(dev)
+
+    def run(ni, fused, t):
+        d_sum = torch.zeros((ni, 7), dtype=torch.float64, device=dev)
+        d_key = torch.zeros(ni, dtype=torch.int64, device=dev)
+        d_nn = torch.zeros(ni, dtype=torch.int32, device=dev)
+        L.g6x_predict(njl, float(t))
+        f = L.g6x_calc_device_allreduce if fused else L.g6x_calc_device
+        f(njl, ni, d_id.data_ptr(), d_x.data_ptr(), d_v.data_ptr(), None, 1e-4, 1, d_sum.data_ptr(), d_key.data_ptr(),
+          d_nn.data_ptr())
+        if not fused:
+            def resolve(keys):
+                L.g6x_resolve_nn(ni, keys.data_ptr(), rank, d_nn.data_ptr())
+                return d_nn
+            d_nn = S.combine_partials(d_sum, d_key, resolve)
+        return d_sum, d_key, d_nn
+
+    ok = True
+    msgs = []
+    for ni in (n, 37, 700, 5000):
+        a_sum, a_key, a_nn = run(ni, False, 0.0)
+        b_sum, b_key, b_nn = run(ni, True, 0.0)
+        torch.cuda.synchronize()
+        if L.g6x_peer_error():
+            ok = False; msgs.append("peer error flag set")
+        # the fused path adds the shards in rank order; NCCL's order is its own: agreement to rounding
+        rel = ((a_sum - b_sum).abs().max() / a_sum.abs().max()).item()
+        same_key = bool((a_key == b_key).all().item())
+        same_nn = bool((a_nn == b_nn).all().item())
+        # every rank must hold the same totals
+        chk = b_sum.clone(); dist.all_reduce(chk, op=dist.ReduceOp.MAX)
+        same_all = bool((chk == b_sum).all().item())
+        if not (rel < 1e-13 and same_key and same_nn and same_all):
+            ok = False
+        msgs.append("ni=%d fused-vs-nccl rel %.1e keys %s nn %s identical-on-all-ranks %s" % (ni, rel, same_key, same_nn, same_all))
+        if rank == 0 and ni <= 5000:
+            from oracle import oracle as O
+            from helpers import check_forces, check_nn
+            ref = O.force(x[:ni], v[:ni], m, x, v, 1e-4, iid=ids[:ni], jid=ids, scales=True)
+            s = b_sum.cpu().numpy()
+            out = dict(acc=s[:, 0:3], jerk=s[:, 3:6], pot=-s[:, 6])
+            try:
+                check_forces(out, ref, what="fused multi-GPU ni=%d" % ni)
+                check_nn(b_nn.cpu().numpy(), ref["nn"], ids, x[:ni], x)
+            except AssertionError as e:
+                ok = False; msgs.append(str(e))
+    # latency of a small block step, both ways
+    for fused in (False, True):
+        for k in range(5):
+            run(37, fused, 1e-6 * (k + 1))
+        torch.cuda.synchronize(); dist.barrier()
+        t0 = time.perf_counter()
+        for k in range(50):
+            r = run(37, fused, 1e-4 + 1e-6 * k)
+            r[0][0, 0].item()      # the caller reads the result every step
+        dt = (time.perf_counter() - t0) / 50
+        msgs.append("block step ni=37 %s: %.1f us" % ("peer-memory exchange" if fused else "3 NCCL all-reduces", dt * 1e6))
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    g.close()
+    if rank == 0:
+        print(("MULTI-GPU OK " if flag.item() else "MULTI-GPU FAILED ") + "world=%d n=%d | " % (world, n) + " | ".join(msgs))
+    dist.destroy_process_group()
+    sys.exit(0 if flag.item() else 1)
+
+
+if __name__ == "__main__":
+    main()
