@@ -391,8 +391,8 @@ __device__ __forceinline__ void interact(const float4 a, const float4 b, const f
             jmin = jaddr;
         }
     }
-    if (LIST) {
-        if (ok && r2 <= h2) {
+    if (LIST) {   // sapporo's rule (dev_evaluate_gravity.cu:60-67): r2 <= h2 and ids differ -- no 2^-52 guard
+        if (idok && r2 <= h2) {
             int pos = atomicAdd(&p.ngb_cnt[i_global], 1);
             if (pos < p.ngb_cap) p.ngb_list[(size_t)i_global * p.ngb_cap + pos] = __float_as_int(b.w);
         }
@@ -468,12 +468,12 @@ __device__ __forceinline__ void interact2(const float4 a, const float4 b, const 
             }
         }
     }
-    if (LIST) {
-        if (ok0 && r20 <= I.h20) {
+    if (LIST) {   // sapporo's rule (dev_evaluate_gravity.cu:60-67): r2 <= h2 and ids differ -- no 2^-52 guard
+        if (id0 && r20 <= I.h20) {
             int pos = atomicAdd(&p.ngb_cnt[i_global0], 1);
             if (pos < p.ngb_cap) p.ngb_list[(size_t)i_global0 * p.ngb_cap + pos] = jid;
         }
-        if (ok1 && r21 <= I.h21) {
+        if (id1 && r21 <= I.h21) {
             int pos = atomicAdd(&p.ngb_cnt[i_global0 + 1], 1);
             if (pos < p.ngb_cap) p.ngb_list[(size_t)(i_global0 + 1) * p.ngb_cap + pos] = jid;
         }

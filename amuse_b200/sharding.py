@@ -79,3 +79,25 @@ def attach_peers(lib, capacity, group=None):
         raise RuntimeError("g6x_peer_attach failed")
     dist.barrier(group=group)
     return world
+
+
+def gather_neighbour_lists(counts, lists, group=None):
+    """Neighbour-sphere lists of an i-block over all j-shards: every rank passes
+    what ``g6_get_neighbour_list_`` returned for ITS shard -- `counts[i]` (full count, may exceed the
+    stored length) and `lists[i]` (sorted ids) -- and gets back, identically on every rank,
+    (total_counts[i], merged sorted ids[i]).  Ids are unique across shards, so the merge of sorted
+    per-shard lists is the list a single device would return (sapporo.cpp:248-272: ascending ids)."""
+    import heapq
+
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return list(counts), [list(l) for l in lists]
+    world = dist.get_world_size(group)
+    mine = ([int(c) for c in counts], [[int(v) for v in l] for l in lists])
+    parts = [None] * world
+    dist.all_gather_object(parts, mine, group=group)
+    ni = len(counts)
+    tot = [sum(parts[r][0][i] for r in range(world)) for i in range(ni)]
+    merged = [list(heapq.merge(*[parts[r][1][i] for r in range(world)])) for i in range(ni)]
+    return tot, merged

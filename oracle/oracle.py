@@ -184,14 +184,16 @@ def ref_predict_force(mass, tj, pos, vel, acc, jerk, t, eps2, ipos, ivel):
     return dict(pred_pos=pp, pred_vel=pv, acc=ia, jerk=ij, pot=ip, nn=inn, dnn=idn, seconds=sec.value)
 
 
-def ref_evolve(mass, pos, vel, eps2, eta, t_end, ids=None, use_gpu=False, libname="libph4ref.so"):
+def ref_evolve(mass, pos, vel, eps2, eta, t_end, ids=None, use_gpu=False, libname="libph4ref.so", max_block_steps=0):
     """Run the reference Hermite integrator (CPU mode, or g6-ABI mode with
     libname='libph4ref_gpu.so' built by ``make -C oracle refgpu``)."""
     n = len(mass)
     L = ref(libname)
     out = np.zeros(8)
     ids_ = _c(ids, np.int32) if ids is not None else None
-    L.ph4ref_evolve(n, ids_.ctypes.data if ids is not None else None, _c(mass), _c(pos), _c(vel),
-                    float(eps2), float(eta), float(t_end), int(use_gpu), out, None, None)
+    L.ph4ref_evolve_steps.argtypes = [C.c_int, C.c_void_p, _dp, _dp, _dp, C.c_double, C.c_double, C.c_double, C.c_int,
+                                      C.c_long, _dp, C.c_void_p, C.c_void_p]
+    L.ph4ref_evolve_steps(n, ids_.ctypes.data if ids is not None else None, _c(mass), _c(pos), _c(vel),
+                          float(eps2), float(eta), float(t_end), int(use_gpu), int(max_block_steps), out, None, None)
     return dict(E0=out[0], E1=out[1], block_steps=int(out[2]), particle_steps=int(out[3]),
                 seconds=out[4], t=out[5])

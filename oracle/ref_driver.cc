@@ -158,9 +158,21 @@ int ph4ref_predict_force(int nj, const double *mass, const double *tj,
 // use_gpu selects the g6 ABI path when compiled -DGPU.
 // out[0]=E0 out[1]=E(t_end) out[2]=block steps out[3]=particle steps
 // out[4]=wall seconds of the advance loop  out[5]=final system_time
+// max_block_steps > 0 bounds the advance loop (config 4: N = 1M with hard binaries takes
+// ~1e8 block steps per time unit; a bounded number of them is timed and extrapolated).
+int ph4ref_evolve_steps(int n, const int *id, const double *mass, const double *pos,
+                        const double *vel, double eps2, double eta, double t_end,
+                        int use_gpu, long max_block_steps, double *out, double *pos_out, double *vel_out);
 int ph4ref_evolve(int n, const int *id, const double *mass, const double *pos,
                   const double *vel, double eps2, double eta, double t_end,
                   int use_gpu, double *out, double *pos_out, double *vel_out)
+{
+    return ph4ref_evolve_steps(n, id, mass, pos, vel, eps2, eta, t_end, use_gpu, 0, out, pos_out, vel_out);
+}
+
+int ph4ref_evolve_steps(int n, const int *id, const double *mass, const double *pos,
+                        const double *vel, double eps2, double eta, double t_end,
+                        int use_gpu, long max_block_steps, double *out, double *pos_out, double *vel_out)
 {
     quiet q;
     jdata jd;
@@ -171,7 +183,7 @@ int ph4ref_evolve(int n, const int *id, const double *mass, const double *pos,
     scheduler sched(&jd);
     jd.E0 = jd.get_energy();
     double t0 = wall();
-    while (jd.system_time < t_end) jd.advance();
+    while (jd.system_time < t_end && (max_block_steps <= 0 || jd.block_steps < max_block_steps)) jd.advance();
     jd.synchronize_all();
     double t1 = wall();
     out[0] = jd.E0;

@@ -48,6 +48,16 @@ def _worker(rank, world, port, n, ni, q):
         s = d_sum.numpy()
         ok = (np.allclose(s[:, 0:3], full["acc"], rtol=1e-12, atol=0) and np.allclose(s[:, 3:6], full["jerk"], rtol=1e-10, atol=1e-13)
               and np.allclose(-s[:, 6], full["pot"], rtol=1e-12) and np.array_equal(nn.numpy(), ids[full["nn"]]))
+        # neighbour-sphere lists: per-shard lists merged over the ranks == the unsharded list
+        h2 = np.minimum(8 * full["dnn"] ** 2, 1.0)
+        cnt, lst = [], []
+        for i in range(ni):
+            c, l = O.neighbours(int(ids[i]), x[i], h2[i], ids[j0:j1], m[j0:j1], x[j0:j1])
+            cnt.append(c); lst.append(l)
+        tot, merged = S.gather_neighbour_lists(cnt, lst)
+        for i in range(ni):
+            c, l = O.neighbours(int(ids[i]), x[i], h2[i], ids, m, x)
+            ok = ok and tot[i] == c and merged[i] == l.tolist()
         q.put((rank, bool(ok), (j0, j1)))
     finally:
         dist.destroy_process_group()
