@@ -148,6 +148,28 @@ struct Context {
     u64 *mir_key[MAX_PEERS] = {};
     int *mir_id[MAX_PEERS] = {};
 
+    // device-resident Hermite step (g6x_hermite_*)
+    struct Hermite {
+        int cap = 0;                         // active particles per pass the buffers hold
+        int *h_ilist = nullptr, *dev_h_ilist = nullptr;        // mapped pinned
+        double *h_olddt = nullptr, *dev_h_olddt = nullptr;     // mapped pinned
+        double *h_outdt = nullptr, *dev_h_outdt = nullptr;     // mapped pinned
+        double *h_outpot = nullptr, *dev_h_outpot = nullptr;
+        int *h_outnn = nullptr, *dev_h_outnn = nullptr;
+        double *d_pred = nullptr;                              // [cap][6]
+        int *d_ilist = nullptr;                                // device copies of the block's addresses / steps
+        double *d_olddt = nullptr;
+        float4 *d_i = nullptr;                                 // [3][cap]
+        double *d_sum = nullptr;                               // [cap][7]
+        u64 *d_key = nullptr;
+        int *d_nnid = nullptr;
+        // integrator state of g6x_hermite_evolve (host side: the scheduler's view)
+        std::vector<double> time, dt;
+        double system_time = 0.0;
+        long long block_steps = 0, particle_steps = 0;
+        bool initialised = false;
+    } herm;
+
     // captured by firsthalf
     int cur_ni = 0, cur_nj = 0;
     float cur_eps2 = 0.f;
@@ -419,6 +441,27 @@ void launch_fast(const ForceArgs &a, dim3 grid, bool nn, cudaStream_t st)
     CK(cudaGetLastError());
 }
 
+// Device-resident Hermite step, small blocks: masked kernels whose final-output stage runs the corrector.
+template <int IPT, int NI_SLOTS, bool PACKED, int MINB>
+void launch_herm(const ForceArgs &a, dim3 grid, cudaStream_t st)
+{
+    size_t smem = sizeof(ForceSmem);
+    static const InlineI<0> none{};
+#define G6_LAUNCH(NR_)                                                                              \
+    do {                                                                                            \
+        auto kern = force_kernel<IPT, NI_SLOTS, true, false, PACKED, NR_, MINB, 0, true>;           \
+        static bool attr_set = false;                                                               \
+        if (!attr_set) {                                                                            \
+            CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            attr_set = true;                                                                        \
+        }                                                                                           \
+        kern<<<grid, THREADS, smem, st>>>(a, none);                                                 \
+    } while (0)
+    if (G.refine) G6_LAUNCH(true); else G6_LAUNCH(false);
+#undef G6_LAUNCH
+    CK(cudaGetLastError());
+}
+
 const VariantInfo &variant_info(int v)
 {
     static const VariantInfo info[V_COUNT] = {
@@ -467,10 +510,14 @@ int choose_variant(int ni, int nj)
 // launch raises G.h_flag = flag_seq when they are complete.
 void launch_force(int nj, int ni, const float4 *iA, const float4 *iB, const float4 *iC, float eps2, bool nn,
                   bool list, double *out_sum, u64 *out_key, int *out_nnid, const float4 *inline_src = nullptr,
-                  unsigned long long flag_seq = 0)
+                  unsigned long long flag_seq = 0, const HermiteArgs *herm = nullptr)
 {
     if (nj > G.capacity) nj = G.capacity;
     int v = choose_variant(ni, nj);
+    if (herm && !(v == V_W1 || v == V_T1 || v == V_P2W)) {
+        fprintf(stderr, "g6_b200: FATAL fused Hermite corrector with variant %d\n", v);
+        exit(-1);
+    }
     if (inline_src && !(v == V_W1 || v == V_T1 || v == V_P2W)) {
         fprintf(stderr, "g6_b200: FATAL inline i-block with variant %d\n", v);
         exit(-1);
@@ -517,7 +564,7 @@ void launch_force(int nj, int ni, const float4 *iA, const float4 *iB, const floa
     // many splits of few i-blocks: sum the partials with a kernel of its own (one warp per i, spread
     // over the SMs) instead of the last CTA -- except for the 4-particle shape, whose last CTA puts
     // 32 lanes on each i
-    const bool defer = (nsplit > 32) && (n_iblocks * 8 <= slots) && (vi.ib > 4);
+    const bool defer = (nsplit > 32) && (n_iblocks * 8 <= slots) && (vi.ib > 4) && !herm;
     a.defer_reduce = defer ? 1 : 0;
     a.eps2 = eps2;
     if (nsplit > 1) ensure_partials((size_t)nsplit * ni);
@@ -539,7 +586,12 @@ void launch_force(int nj, int ni, const float4 *iA, const float4 *iB, const floa
         a.flag_seq = flag_seq;
         a.done_expected = defer ? (unsigned)reduce_ctas : (unsigned)n_iblocks;
     }
-    if (inline_src) {
+    if (herm) {
+        a.herm = *herm;
+        if (v == V_T1) launch_herm<1, 4, false, 2>(a, grid, G.stream);
+        else if (v == V_W1) launch_herm<1, 32, false, 2>(a, grid, G.stream);
+        else launch_herm<2, 32, true, 2>(a, grid, G.stream);
+    } else if (inline_src) {
         if (ni <= 64) {
             InlineI<64> ii;
             for (int k = 0; k < 3; k++) memcpy(ii.d + 64 * k, inline_src + (size_t)ni * k, sizeof(float4) * ni);
@@ -593,6 +645,15 @@ void free_all()
     host_free(G.h_sum);
     host_free(G.h_flag);
     dev_free(G.d_done);
+    {
+        Context::Hermite &H = G.herm;
+        host_free(H.h_ilist); host_free(H.h_olddt); host_free(H.h_outdt); host_free(H.h_outpot); host_free(H.h_outnn);
+        dev_free(H.d_pred); dev_free(H.d_i); dev_free(H.d_sum); dev_free(H.d_key); dev_free(H.d_nnid);
+        dev_free(H.d_ilist); dev_free(H.d_olddt);
+        H.cap = 0;
+        H.time.clear(); H.dt.clear();
+        H.initialised = false;
+    }
     G.dev_h_sum = nullptr; G.dev_h_flag = nullptr; G.dev_h_up2[0] = G.dev_h_up2[1] = nullptr;
     G.cur_direct = false; G.i_on_device = false;
     dev_free(G.part_sum); dev_free(G.part_key); dev_free(G.tickets);
@@ -1270,6 +1331,222 @@ int g6x_resolve_nn(int ni, const unsigned long long *d_key, int rank, int *d_nni
                                                                std::min(G.nj_hi, G.capacity), G.js.B, d_nnid);
     G.launches++;
     CK(cudaGetLastError());
+    return 0;
+}
+
+// ---- device-resident Hermite block step -----------------------------------------------------------
+static void hermite_reserve(int n)
+{
+    Context::Hermite &H = G.herm;
+    if (n <= H.cap) return;
+    CK(cudaStreamSynchronize(G.stream));
+    int cap = std::max(n, std::max(4096, 2 * H.cap));
+    host_free(H.h_ilist); host_free(H.h_olddt); host_free(H.h_outdt); host_free(H.h_outpot); host_free(H.h_outnn);
+    dev_free(H.d_pred); dev_free(H.d_i); dev_free(H.d_sum); dev_free(H.d_key); dev_free(H.d_nnid);
+    dev_free(H.d_ilist); dev_free(H.d_olddt);
+    dev_alloc(H.d_ilist, (size_t)cap);
+    dev_alloc(H.d_olddt, (size_t)cap);
+    host_alloc(H.h_ilist, cap);   H.dev_h_ilist = dev_alias(H.h_ilist);
+    host_alloc(H.h_olddt, cap);   H.dev_h_olddt = dev_alias(H.h_olddt);
+    host_alloc(H.h_outdt, cap);   H.dev_h_outdt = dev_alias(H.h_outdt);
+    host_alloc(H.h_outpot, cap);  H.dev_h_outpot = dev_alias(H.h_outpot);
+    host_alloc(H.h_outnn, cap);   H.dev_h_outnn = dev_alias(H.h_outnn);
+    dev_alloc(H.d_pred, (size_t)6 * cap);
+    dev_alloc(H.d_i, (size_t)3 * cap);
+    dev_alloc(H.d_sum, (size_t)7 * cap);
+    dev_alloc(H.d_key, (size_t)cap);
+    dev_alloc(H.d_nnid, (size_t)cap);
+    H.cap = cap;
+}
+
+// One pass over n <= cap active particles whose addresses / old steps are already in H.h_ilist / H.h_olddt.
+// Blocks until the results are in H.h_outdt / h_outpot / h_outnn.
+static void hermite_pass(int nj, int n, double tnext, double eta, double eps2, int mode)
+{
+    Context::Hermite &H = G.herm;
+    HermiteArgs h{};
+    h.ni = n;
+    h.ilist = H.dev_h_ilist;
+    h.old_dt = H.dev_h_olddt;
+    h.ilist_d = H.d_ilist;
+    h.olddt_d = H.d_olddt;
+    h.tnext = tnext;
+    h.eta = eta;
+    h.js = G.js;
+    h.iA = H.d_i; h.iB = H.d_i + n; h.iC = H.d_i + 2 * (size_t)n;
+    h.pred = H.d_pred;
+    h.sum = H.d_sum;
+    h.nnid = H.d_nnid;
+    h.out_dt = H.dev_h_outdt; h.out_pot = H.dev_h_outpot; h.out_nn = H.dev_h_outnn;
+    h.mode = mode;
+    h.done_counter = G.d_done;
+    h.host_flag = G.dev_h_flag;
+    h.flag_seq = ++G.flag_seq;
+    const int ctas = (n + 255) / 256;
+    G.ti = tnext;
+    if (n <= 384 && G.variant == V_AUTO) {
+        // small block: two launches -- (predict all j + gather/predict the block), then the force kernel
+        // whose final-output stage is the corrector
+        const int njc = std::min(nj, G.capacity);
+        const int npred = std::max(njc, std::min(G.nj_hi, G.capacity));
+        const int ntiles = (npred + TILE - 1) / TILE;
+        hermite_predict_gather_kernel<<<ntiles + ctas, TILE, 0, G.stream>>>(ntiles, npred, tnext, h);
+        CK(cudaGetLastError());
+        G.predicted_nj = npred;
+        G.predicted_ti = tnext;
+        G.j_dirty = false;
+        launch_force(nj, n, h.iA, h.iB, h.iC, (float)eps2, true, false, H.d_sum, H.d_key, H.d_nnid, nullptr,
+                     h.flag_seq, &h);
+        G.launches += 1;
+    } else {
+        hermite_gather_kernel<<<ctas, 256, 0, G.stream>>>(h);
+        CK(cudaGetLastError());
+        run_predictor(nj);
+        launch_force(nj, n, h.iA, h.iB, h.iC, (float)eps2, true, false, H.d_sum, H.d_key, H.d_nnid);
+        hermite_correct_kernel<<<ctas, 256, 0, G.stream>>>(h);
+        CK(cudaGetLastError());
+        G.launches += 2;
+    }
+    G.j_dirty = true;   // the active particles' state changed: predict again before the next force
+    volatile unsigned long long *flag = G.h_flag;
+    unsigned long long spins = 0;
+    while (*flag != h.flag_seq) {
+        if ((++spins & 0xfffff) == 0) {
+            cudaError_t q = cudaStreamQuery(G.stream);
+            if (q == cudaSuccess) {
+                if (*flag == h.flag_seq) break;
+                fprintf(stderr, "g6_b200: FATAL Hermite step finished without raising its completion flag\n");
+                exit(-1);
+            }
+            if (q != cudaErrorNotReady) CK(q);
+        }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+}
+
+int g6x_hermite_step(int nj, int ni, const int *ilist, double tnext, double eta, double eps2, const double *old_dt,
+                     double *new_dt, double *pot, int *nn)
+{
+    require_open("g6x_hermite_step");
+    Context::Hermite &H = G.herm;
+    if (G.pending) CK(cudaStreamSynchronize(G.stream));
+    flush_updates();
+    const int chunk = G.npipes;
+    hermite_reserve(std::min(ni, chunk));
+    // every chunk reads the state the previous chunk already corrected, exactly like ph4 would if it
+    // split a block (it does not: blocks above npipes only occur in synchronised (re)starts)
+    for (int i0 = 0; i0 < ni; i0 += chunk) {
+        const int n = std::min(chunk, ni - i0);
+        memcpy(H.h_ilist, ilist + i0, sizeof(int) * n);
+        memcpy(H.h_olddt, old_dt + i0, sizeof(double) * n);
+        hermite_pass(nj, n, tnext, eta, eps2, 0);
+        memcpy(new_dt + i0, H.h_outdt, sizeof(double) * n);
+        if (pot) memcpy(pot + i0, H.h_outpot, sizeof(double) * n);
+        if (nn) memcpy(nn + i0, H.h_outnn, sizeof(int) * n);
+    }
+    return 0;
+}
+
+int g6x_hermite_init(int nj, double t0, double eta, double eps2, double *timestep_out)
+{
+    require_open("g6x_hermite_init");
+    Context::Hermite &H = G.herm;
+    if (G.pending) CK(cudaStreamSynchronize(G.stream));
+    flush_updates();
+    nj = std::min(nj, G.capacity);
+    const int chunk = G.npipes;
+    hermite_reserve(std::min(nj, chunk));
+    H.time.assign(nj, t0);
+    H.dt.assign(nj, 0.0);
+    // forces of all particles at t0 against the state as it is; acc/jerk only enter the predictor for
+    // dt != 0, and all particles sit at t0, so writing them chunk by chunk does not change later chunks
+    for (int i0 = 0; i0 < nj; i0 += chunk) {
+        const int n = std::min(chunk, nj - i0);
+        for (int k = 0; k < n; k++) H.h_ilist[k] = i0 + k;
+        hermite_pass(nj, n, t0, eta, eps2, 1);
+        memcpy(H.dt.data() + i0, H.h_outdt, sizeof(double) * n);
+    }
+    if (timestep_out) memcpy(timestep_out, H.dt.data(), sizeof(double) * nj);
+    H.system_time = t0;
+    H.block_steps = H.particle_steps = 0;
+    H.initialised = true;
+    return 0;
+}
+
+// ph4's jdata::advance loop (jdata.cc:752-795) with the scheduler on the host (a heap of next times;
+// the reference keeps a sorted list, scheduler.cc) and everything else on the device.
+// stats[0] = system time reached, [1] = block steps, [2] = particle steps, [3] = wall seconds.
+long long g6x_hermite_evolve(int nj, double t_end, double eta, double eps2, long long max_block_steps, double *stats)
+{
+    require_open("g6x_hermite_evolve");
+    Context::Hermite &H = G.herm;
+    if (!H.initialised || (int)H.time.size() != std::min(nj, G.capacity)) {
+        fprintf(stderr, "g6_b200: FATAL g6x_hermite_evolve before g6x_hermite_init\n");
+        exit(-1);
+    }
+    nj = (int)H.time.size();
+    typedef std::pair<double, int> Ev;
+    std::vector<Ev> heap;
+    heap.reserve(nj);
+    for (int j = 0; j < nj; j++) heap.push_back(Ev(H.time[j] + H.dt[j], j));
+    auto later = [](const Ev &a, const Ev &b) { return a.first > b.first || (a.first == b.first && a.second > b.second); };
+    std::make_heap(heap.begin(), heap.end(), later);
+    std::vector<int> ilist;
+    std::vector<double> olddt, newdt;
+    const double w0 = wall();
+    long long steps = 0;
+    while (H.system_time < t_end && (max_block_steps <= 0 || steps < max_block_steps)) {
+        const double tnext = heap.front().first;
+        ilist.clear();
+        while (!heap.empty() && heap.front().first == tnext) {
+            std::pop_heap(heap.begin(), heap.end(), later);
+            ilist.push_back(heap.back().second);
+            heap.pop_back();
+        }
+        const int ni = (int)ilist.size();
+        olddt.resize(ni);
+        newdt.resize(ni);
+        for (int k = 0; k < ni; k++) olddt[k] = H.dt[ilist[k]];
+        g6x_hermite_step(nj, ni, ilist.data(), tnext, eta, eps2, olddt.data(), newdt.data(), nullptr, nullptr);
+        for (int k = 0; k < ni; k++) {
+            const int j = ilist[k];
+            H.time[j] = tnext;
+            H.dt[j] = newdt[k];
+            heap.push_back(Ev(tnext + newdt[k], j));
+            std::push_heap(heap.begin(), heap.end(), later);
+        }
+        H.system_time = tnext;
+        H.block_steps++;
+        H.particle_steps += ni;
+        steps++;
+    }
+    if (stats) {
+        stats[0] = H.system_time;
+        stats[1] = (double)H.block_steps;
+        stats[2] = (double)H.particle_steps;
+        stats[3] = wall() - w0;
+    }
+    return steps;
+}
+
+int g6x_hermite_get_state(int nj, double *t, double (*x)[3], double (*v)[3], double (*a)[3], double (*j)[3])
+{
+    require_open("g6x_hermite_get_state");
+    flush_updates();
+    nj = std::min(nj, G.capacity);
+    std::vector<double2> q[7];
+    CK(cudaStreamSynchronize(G.stream));
+    for (int k = 0; k < 7; k++) {
+        q[k].resize(nj);
+        CK(cudaMemcpy(q[k].data(), G.js.q[k], sizeof(double2) * nj, cudaMemcpyDeviceToHost));
+    }
+    for (int i = 0; i < nj; i++) {
+        if (x) { x[i][0] = q[0][i].x; x[i][1] = q[0][i].y; x[i][2] = q[1][i].x; }
+        if (t) t[i] = q[1][i].y;
+        if (v) { v[i][0] = q[2][i].x; v[i][1] = q[2][i].y; v[i][2] = q[3][i].x; }
+        if (a) { a[i][0] = q[3][i].y; a[i][1] = q[4][i].x; a[i][2] = q[4][i].y; }
+        if (j) { j[i][0] = q[5][i].x; j[i][1] = q[5][i].y; j[i][2] = q[6][i].x; }
+    }
     return 0;
 }
 

@@ -268,6 +268,28 @@ __device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c)
 // ---------------------------------------------------------------------------
 // Force kernel.
 // ---------------------------------------------------------------------------
+// Arguments of the device-resident Hermite step (see "Device-resident Hermite block step" below).
+struct HermiteArgs {
+    int ni;
+    const int *ilist;          // j-addresses of the active particles (mapped pinned host memory or device)
+    const double *old_dt;      // their current time steps (same memory); unused by the init pass
+    int *ilist_d;              // device copies made by the gather pass, read by the corrector
+    double *olddt_d;
+    double tnext, eta;
+    JState js;
+    float4 *iA, *iB, *iC;      // packed i-block for the force kernels
+    double *pred;              // [ni][6] predicted pos, vel (FP64) kept for the corrector
+    const double *sum;         // [ni][7] force-kernel output: acc, jerk, +sum m/r
+    const int *nnid;           // [ni]
+    double *out_dt;            // [ni] new time step          (mapped pinned host memory)
+    double *out_pot;           // [ni] potential (negative)   (mapped pinned host memory)
+    int *out_nn;               // [ni] id of the nearest neighbour
+    int mode;                  // 0: corrector;  1: initialisation (a, j <- forces; first time step, jdata.cc:503-548)
+    unsigned int *done_counter;
+    unsigned long long *host_flag;
+    unsigned long long flag_seq;
+};
+
 constexpr int MAX_PEERS = 7;   // other ranks of one NVSwitch domain (8 GPUs)
 struct ForceArgs {
     const float4 *jA, *jB, *jC;   // predicted j (device)
@@ -296,6 +318,9 @@ struct ForceArgs {
     // multi-GPU exchange fused into the force kernel: whoever writes final outputs of this rank's
     // j-shard also stores them into its slot of every peer's exchange buffer over NVLink (peer pointers
     // from CUDA IPC), so the partials travel while the other i-blocks are still being computed
+    // device-resident Hermite step, small blocks: whoever writes particle i's final force also runs its
+    // corrector (HERM kernels), so a block step is two launches (predict+gather, force+correct)
+    HermiteArgs herm;
     int n_mirror;
     double *m_sum[MAX_PEERS];            // [ni][7] at each peer, already offset to this launch's first i
     u64 *m_key[MAX_PEERS];
@@ -309,21 +334,27 @@ struct InlineI {
     float4 d[3 * (N > 0 ? N : 1)];
 };
 
+__device__ __forceinline__ void hermite_correct_one(const HermiteArgs &h, const int i, const double *f, const int nnid);
+
 // Final outputs of particle i (local arrays + the peers' exchange slots).
-template <bool NN>
+template <bool NN, bool HERM = false>
 __device__ __forceinline__ void store_outputs(const ForceArgs &p, const int i, const double *tot, const u64 kk)
 {
     int id = -1;
     if (NN && kk != KEY_NONE) id = __float_as_int(p.jB[(int)(unsigned)(kk & 0xffffffffu) - p.j_offset].w);
+    if (HERM) {   // the particle's force is complete: correct it right here
+        hermite_correct_one(p.herm, i, tot, id);
+    } else {
 #pragma unroll
-    for (int q = 0; q < 7; q++) p.out_sum[(size_t)i * 7 + q] = tot[q];
-    p.out_key[i] = kk;
-    if (NN) p.out_nnid[i] = id;
-    for (int m = 0; m < p.n_mirror; m++) {
+        for (int q = 0; q < 7; q++) p.out_sum[(size_t)i * 7 + q] = tot[q];
+        p.out_key[i] = kk;
+        if (NN) p.out_nnid[i] = id;
+        for (int m = 0; m < p.n_mirror; m++) {
 #pragma unroll
-        for (int q = 0; q < 7; q++) p.m_sum[m][(size_t)i * 7 + q] = tot[q];
-        p.m_key[m][i] = kk;
-        p.m_id[m][i] = id;
+            for (int q = 0; q < 7; q++) p.m_sum[m][(size_t)i * 7 + q] = tot[q];
+            p.m_key[m][i] = kk;
+            p.m_id[m][i] = id;
+        }
     }
 }
 
@@ -486,7 +517,7 @@ __device__ __forceinline__ void interact2(const float4 a, const float4 b, const 
 // subset of the splits, and a fixed butterfly of shuffles combines them -- the block-timestep regime
 // has hundreds of splits of a handful of i, which one thread per i would walk serially.  Both orders
 // are fixed, so results are deterministic.
-template <bool NN>
+template <bool NN, bool HERM = false>
 __device__ __forceinline__ void reduce_splits(const ForceArgs &p, unsigned int *is_last, const int IB)
 {
     const int tid = threadIdx.x;
@@ -500,7 +531,7 @@ __device__ __forceinline__ void reduce_splits(const ForceArgs &p, unsigned int *
     __syncthreads();
     if (!*is_last) return;
     __threadfence();
-    auto write_out = [&](int i, const double *tot, u64 kk) { store_outputs<NN>(p, i, tot, kk); };
+    auto write_out = [&](int i, const double *tot, u64 kk) { store_outputs<NN, HERM>(p, i, tot, kk); };
     if (IB >= THREADS) {
         for (int il = tid; il < IB; il += THREADS) {
             int i = blockIdx.y * IB + il;
@@ -606,7 +637,7 @@ __device__ __forceinline__ u64 make_key(float r2min, int jmin_global)
 // partial sums are flushed to FP64 so that long sums keep ~1e-7 accuracy.
 // Partials of the j-slots are reduced with warp shuffles + shared memory, and the
 // partials of the j-splits by the last CTA to arrive (ticket), in fixed order.
-template <int IPT, int NI_SLOTS, bool NN, bool LIST, bool PACKED, bool NR, int MINB, int INL>
+template <int IPT, int NI_SLOTS, bool NN, bool LIST, bool PACKED, bool NR, int MINB, int INL, bool HERM = false>
 __global__ void __launch_bounds__(THREADS, MINB) force_kernel(const ForceArgs p,
                                                               const __grid_constant__ InlineI<INL> ii)
 {
@@ -840,7 +871,7 @@ __global__ void __launch_bounds__(THREADS, MINB) force_kernel(const ForceArgs p,
         int i = blockIdx.y * IB + il;
         if (i >= p.ni) return;
         if (single) {
-            store_outputs<NN>(p, i, tot, kk);
+            store_outputs<NN, HERM>(p, i, tot, kk);
         } else {
             size_t o = (size_t)blockIdx.x * p.ni_pad + i;
 #pragma unroll
@@ -870,7 +901,7 @@ __global__ void __launch_bounds__(THREADS, MINB) force_kernel(const ForceArgs p,
     }
     if (single) signal_done(p);
     if (single || p.defer_reduce) return;
-    reduce_splits<NN>(p, &sm.is_last, IB);
+    reduce_splits<NN, HERM>(p, &sm.is_last, IB);
 }
 
 // ---------------------------------------------------------------------------
@@ -1259,6 +1290,152 @@ __global__ void resolve_nn_kernel(int ni, const u64 *__restrict__ key, int rank,
         if (a >= 0 && a < nj_local) id = __float_as_int(jB[a].w);
     }
     nnid[i] = id;
+}
+
+// ---------------------------------------------------------------------------
+// Device-resident Hermite block step (the steps either side of the force call in ph4's
+// idata::advance, src/amuse_ph4/src/idata.cc:832-870): the active particles ARE j-particles, so their
+// state is gathered from the j-memory, predicted (idata.cc:347-365), pushed through the force kernels,
+// corrected with the Aarseth step and its block quantisation (idata.cc:443-511), and written back
+// into the j-memory -- no host round trip of positions, no per-particle g6_set_j_particle.
+// All of this is FP64 with the reference's expression trees.
+// ---------------------------------------------------------------------------
+
+__device__ __forceinline__ void hermite_gather_one(const HermiteArgs &h, const int i)
+{
+    const int a = h.ilist[i];
+    const JState &s = h.js;
+    const double2 q0 = s.q[0][a], q1 = s.q[1][a], q2 = s.q[2][a], q3 = s.q[3][a], q4 = s.q[4][a], q5 = s.q[5][a],
+                  q6 = s.q[6][a];
+    const double x = q0.x, y = q0.y, z = q1.x, tj = q1.y, vx = q2.x, vy = q2.y, vz = q3.x;
+    const double ax = q3.y, ay = q4.x, az = q4.y, jx = q5.x, jy = q5.y, jz = q6.x;
+    const int id = __double2hiint(q6.y);
+    const double dt = h.tnext - tj;
+    double px = x, py = y, pz = z, qx = vx, qy = vy, qz = vz;
+    if (dt != 0.0) {  // idata.cc:353-361
+        px = x + dt * (vx + 0.5 * dt * (ax + dt * jx / 3));
+        py = y + dt * (vy + 0.5 * dt * (ay + dt * jy / 3));
+        pz = z + dt * (vz + 0.5 * dt * (az + dt * jz / 3));
+        qx = vx + dt * (ax + 0.5 * dt * jx);
+        qy = vy + dt * (ay + 0.5 * dt * jy);
+        qz = vz + dt * (az + 0.5 * dt * jz);
+    }
+    double *pr = h.pred + (size_t)i * 6;
+    pr[0] = px; pr[1] = py; pr[2] = pz; pr[3] = qx; pr[4] = qy; pr[5] = qz;
+    h.ilist_d[i] = a;
+    h.olddt_d[i] = (h.mode == 0) ? h.old_dt[i] : 0.0;
+    const float xh = (float)px, yh = (float)py, zh = (float)pz;
+    h.iA[i] = make_float4(xh, yh, zh, 0.f);
+    h.iB[i] = make_float4((float)(px - (double)xh), (float)(py - (double)yh), (float)(pz - (double)zh),
+                          __int_as_float(id));
+    h.iC[i] = make_float4((float)qx, (float)qy, (float)qz, 0.f);
+}
+
+// Corrector (or initialisation) of active particle i given its new force f[7] and neighbour id.
+__device__ __forceinline__ void hermite_correct_one(const HermiteArgs &h, const int i, const double *f, const int nnid)
+{
+    const int a = h.ilist_d[i];
+    const JState &s = h.js;
+    const double2 q1 = s.q[1][a], q3 = s.q[3][a], q4 = s.q[4][a], q5 = s.q[5][a], q6 = s.q[6][a];
+    const double told = q1.y;
+    const double oa[3] = {q3.y, q4.x, q4.y}, oj[3] = {q5.x, q5.y, q6.x};
+    const double ia[3] = {f[0], f[1], f[2]}, ij[3] = {f[3], f[4], f[5]};
+    const double *pr = h.pred + (size_t)i * 6;
+    double pos[3] = {pr[0], pr[1], pr[2]}, vel[3] = {pr[3], pr[4], pr[5]};
+    double newstep;
+    if (h.mode == 0) {   // idata.cc:443-511
+        const double dt = h.tnext - told;
+        const double dt2 = dt * dt;
+        double a2 = 0, j2 = 0, k2 = 0, l2 = 0;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const double alpha = -3 * (oa[k] - ia[k]) - dt * (2 * oj[k] + ij[k]);
+            const double beta = 2 * (oa[k] - ia[k]) + dt * (oj[k] + ij[k]);
+            pos[k] += (alpha / 12 + beta / 20) * dt2;
+            vel[k] += (alpha / 3 + beta / 4) * dt;
+            a2 += ia[k] * ia[k];
+            j2 += (dt * ij[k]) * (dt * ij[k]);
+            k2 += (2 * alpha) * (2 * alpha);
+            l2 += (6 * beta) * (6 * beta);
+        }
+        newstep = h.eta * dt * sqrt((sqrt(a2 * k2) + j2) / (sqrt(j2 * l2) + k2));
+        int exponent;
+        const double olddt = h.olddt_d[i];
+        double oldstep2 = olddt / (2 * frexp(olddt, &exponent));
+        while (fmod(h.tnext, oldstep2) != 0) oldstep2 /= 2;
+        if (newstep < oldstep2) {
+            newstep = oldstep2 / 2;
+        } else {
+            const double t2 = 2 * oldstep2;
+            newstep = (newstep >= t2 && fmod(h.tnext, t2) == 0) ? t2 : oldstep2;
+        }
+    } else {             // jdata.cc:503-548 (fac 0.0625, limit 0.03125)
+        double a2 = 0, j2 = 0;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            a2 += ia[k] * ia[k];
+            j2 += ij[k] * ij[k];
+        }
+        const double fac = 0.0625, limit = 0.03125;
+        double first = (h.eta == 0.0) ? limit : ((a2 == 0.0 || j2 == 0.0) ? fac * h.eta : fac * h.eta * sqrt(a2 / j2));
+        if (first != first) first = fac * h.eta;
+        int exponent;
+        first /= 2 * frexp(first, &exponent);
+        while (fmod(h.tnext, first) != 0) first /= 2;
+        while (first > limit) first /= 2;
+        newstep = first;
+    }
+    s.q[0][a] = make_double2(pos[0], pos[1]);
+    s.q[1][a] = make_double2(pos[2], h.tnext);
+    s.q[2][a] = make_double2(vel[0], vel[1]);
+    s.q[3][a] = make_double2(vel[2], ia[0]);
+    s.q[4][a] = make_double2(ia[1], ia[2]);
+    s.q[5][a] = make_double2(ij[0], ij[1]);
+    s.q[6][a] = make_double2(ij[2], q6.y);
+    h.out_dt[i] = newstep;
+    h.out_pot[i] = -f[6];
+    h.out_nn[i] = nnid;
+}
+
+__global__ void __launch_bounds__(256) hermite_gather_kernel(const HermiteArgs h)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < h.ni) hermite_gather_one(h, i);
+}
+
+__global__ void __launch_bounds__(256) hermite_correct_kernel(const HermiteArgs h)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < h.ni) hermite_correct_one(h, i, h.sum + (size_t)i * 7, h.nnid[i]);
+    // completion flag in mapped host memory (same protocol as signal_done)
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0 && h.host_flag) {
+        bool last = true;
+        if (gridDim.x > 1) {
+            const unsigned int k = atomicAdd(h.done_counter, 1u);
+            last = (k == gridDim.x - 1u);
+            if (last) *h.done_counter = 0u;
+        }
+        if (last) {
+            __threadfence_system();
+            *reinterpret_cast<volatile unsigned long long *>(h.host_flag) = h.flag_seq;
+        }
+    }
+}
+
+// predict all j tiles AND gather/predict the active particles in one launch:
+// CTAs [0, ntiles) predict a tile each, the CTAs after them take 256 active particles each.
+__global__ void __launch_bounds__(TILE) hermite_predict_gather_kernel(const int ntiles, const int n, const double ti,
+                                                                      const HermiteArgs h)
+{
+    __shared__ int sh_lo[TILE / 32], sh_hi[TILE / 32];
+    if ((int)blockIdx.x < ntiles) {
+        predict_tile(blockIdx.x, n, ti, h.js, sh_lo, sh_hi);
+        return;
+    }
+    const int i = (blockIdx.x - ntiles) * TILE + threadIdx.x;
+    if (i < h.ni) hermite_gather_one(h, i);
 }
 
 // ---------------------------------------------------------------------------

@@ -196,6 +196,29 @@ int g6x_device_chunk(int ni);
  * if there is no neighbour.  Mirrors idata.cc:308-313. */
 int g6x_resolve_nn(int ni, const unsigned long long *d_key, int rank,
                    int *d_nnid);
+/* ---- device-resident Hermite block step (the steps either side of the force call) ----
+ * ph4's idata::advance (idata.cc:832-870) gathers the active particles from its j-arrays, predicts
+ * them, calls the g6 library, corrects them, and sends them back one g6_set_j_particle_ at a time.
+ * The active particles ARE j-particles, so the library can do all of that where the state lives:
+ *   g6x_hermite_init : forces on all nj particles at t0 (acc, jerk stored in the j-memory) and first
+ *                      time steps (jdata::set_initial_timestep, jdata.cc:503-548) -> timestep_out[nj]
+ *   g6x_hermite_step : for the ni addresses in ilist: predict to tnext (idata.cc:347-365), force
+ *                      against all j predicted to tnext, corrector + Aarseth step with block
+ *                      quantisation (idata.cc:443-511), state written back.  Host traffic: ilist and
+ *                      old_dt in, new_dt (and optionally pot, nn ids) out.
+ *   g6x_hermite_evolve : jdata::advance loop (jdata.cc:752-795), scheduler on the host, to t_end or
+ *                      max_block_steps (> 0); returns block steps done, stats[4] = time reached,
+ *                      block steps, particle steps (both cumulative), wall seconds of this call.
+ *   g6x_hermite_get_state : copy time/pos/vel/acc/jerk of the j-memory back (any pointer may be NULL).
+ * Single j-shard only (the whole system on this device). */
+int g6x_hermite_init(int nj, double t0, double eta, double eps2, double *timestep_out);
+int g6x_hermite_step(int nj, int ni, const int *ilist, double tnext, double eta,
+                     double eps2, const double *old_dt, double *new_dt, double *pot,
+                     int *nn);
+long long g6x_hermite_evolve(int nj, double t_end, double eta, double eps2,
+                             long long max_block_steps, double *stats);
+int g6x_hermite_get_state(int nj, double *t, double (*x)[3], double (*v)[3],
+                          double (*a)[3], double (*j)[3]);
 /* Block until the library stream is idle. */
 int g6x_synchronize(void);
 /* Cumulative number of CUDA kernels this library has launched. */

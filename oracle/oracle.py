@@ -184,6 +184,28 @@ def ref_predict_force(mass, tj, pos, vel, acc, jerk, t, eps2, ipos, ivel):
     return dict(pred_pos=pp, pred_vel=pv, acc=ia, jerk=ij, pot=ip, nn=inn, dnn=idn, seconds=sec.value)
 
 
+def correct(tnext, eta, itime, itimestep, old_acc, old_jerk, iacc, ijerk, ipos, ivel, use_ref=False):
+    """idata::correct restatement (or the reference itself with use_ref): returns
+    (pos, vel, time, timestep) after the corrector."""
+    ni = len(itime)
+    t = _c(itime).copy(); dt = _c(itimestep).copy(); p = _c(ipos).copy(); v = _c(ivel).copy()
+    L = ref() if use_ref else lib()
+    f = L.ph4ref_correct if use_ref else L.oracle_correct
+    f.argtypes = [C.c_int, C.c_double, C.c_double, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp]
+    f(ni, float(tnext), float(eta), t, dt, _c(old_acc), _c(old_jerk), _c(iacc), _c(ijerk), p, v)
+    return p, v, t, dt
+
+
+def initial_timestep(system_time, eta, acc, jerk):
+    """jdata::set_initial_timestep restatement (jdata.cc:503-548)."""
+    n = len(acc)
+    out = np.zeros(n)
+    L = lib()
+    L.oracle_initial_timestep.argtypes = [C.c_int, C.c_double, C.c_double, _dp, _dp, _dp]
+    L.oracle_initial_timestep(n, float(system_time), float(eta), _c(acc), _c(jerk), out)
+    return out
+
+
 def ref_evolve(mass, pos, vel, eps2, eta, t_end, ids=None, use_gpu=False, libname="libph4ref.so", max_block_steps=0):
     """Run the reference Hermite integrator (CPU mode, or g6-ABI mode with
     libname='libph4ref_gpu.so' built by ``make -C oracle refgpu``)."""

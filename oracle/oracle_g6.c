@@ -245,3 +245,72 @@ int oracle_neighbours(int iid, const double *ipos, double h2, int j_start,
     free(tmp);
     return n;
 }
+
+/*
+ * Hermite corrector and Aarseth time step with block quantisation, follows
+ * idata::correct(), src/amuse_ph4/src/idata.cc:443-511 (the "#else" branch in use).
+ * ipos/ivel: predicted on entry, corrected on exit; itime/itimestep updated in place.
+ */
+void oracle_correct(int ni, double tnext, double eta, double *itime, double *itimestep,
+                    const double *old_acc, const double *old_jerk, const double *iacc,
+                    const double *ijerk, double *ipos, double *ivel)
+{
+    for (int i = 0; i < ni; i++) {
+        double dt = tnext - itime[i];
+        double dt2 = dt * dt;
+        double a2 = 0, j2 = 0, k2 = 0, l2 = 0;
+        for (int k = 0; k < 3; k++) {
+            int q = 3 * i + k;
+            double alpha = -3 * (old_acc[q] - iacc[q]) - dt * (2 * old_jerk[q] + ijerk[q]);
+            double beta = 2 * (old_acc[q] - iacc[q]) + dt * (old_jerk[q] + ijerk[q]);
+            ipos[q] += (alpha / 12 + beta / 20) * dt2;
+            ivel[q] += (alpha / 3 + beta / 4) * dt;
+            a2 += iacc[q] * iacc[q];
+            j2 += (dt * ijerk[q]) * (dt * ijerk[q]);
+            k2 += (2 * alpha) * (2 * alpha);
+            l2 += (6 * beta) * (6 * beta);
+        }
+        double newstep = eta * dt * sqrt((sqrt(a2 * k2) + j2) / (sqrt(j2 * l2) + k2));
+        int exponent;
+        double oldstep2 = itimestep[i] / (2 * frexp(itimestep[i], &exponent));
+        while (fmod(tnext, oldstep2) != 0) oldstep2 /= 2;
+        if (newstep < oldstep2) {
+            newstep = oldstep2 / 2;
+        } else {
+            double t2 = 2 * oldstep2;
+            if (newstep >= t2 && fmod(tnext, t2) == 0)
+                newstep = t2;
+            else
+                newstep = oldstep2;
+        }
+        itime[i] = tnext;
+        itimestep[i] = newstep;
+    }
+}
+
+/*
+ * First time step, follows jdata::set_initial_timestep(), src/amuse_ph4/src/jdata.cc:503-548
+ * (fac = 0.0625, limit = 0.03125, no median limit).
+ */
+void oracle_initial_timestep(int nj, double system_time, double eta, const double *acc, const double *jerk,
+                             double *timestep)
+{
+    const double fac = 0.0625, limit = 0.03125;
+    for (int j = 0; j < nj; j++) {
+        double a2 = 0, j2 = 0;
+        for (int k = 0; k < 3; k++) {
+            a2 += acc[3 * j + k] * acc[3 * j + k];
+            j2 += jerk[3 * j + k] * jerk[3 * j + k];
+        }
+        double firststep;
+        if (eta == 0.0) firststep = limit;
+        else if (a2 == 0.0 || j2 == 0.0) firststep = fac * eta;
+        else firststep = fac * eta * sqrt(a2 / j2);
+        if (firststep != firststep) firststep = fac * eta;
+        int exponent;
+        firststep /= 2 * frexp(firststep, &exponent);
+        while (fmod(system_time, firststep) != 0) firststep /= 2;
+        while (firststep > limit) firststep /= 2;
+        timestep[j] = firststep;
+    }
+}

@@ -153,6 +153,44 @@ int ph4ref_predict_force(int nj, const double *mass, const double *tj,
     return 0;
 }
 
+// The reference corrector + Aarseth step with block quantisation, idata::correct()
+// (src/amuse_ph4/src/idata.cc:399-514), on caller-supplied i-data.  ipos/ivel come in as the
+// predicted values and go out corrected; itime/itimestep are updated in place.
+int ph4ref_correct(int ni, double tnext, double eta, double *itime, double *itimestep,
+                   const double *old_acc, const double *old_jerk, const double *iacc, const double *ijerk,
+                   double *ipos, double *ivel)
+{
+    quiet q;
+    jdata jd;
+    jd.eta = eta;
+    idata id_;
+    id_.jdat = &jd;
+    id_.set_ni(ni);
+    id_.ni = ni;
+    for (int i = 0; i < ni; i++) {
+        id_.itime[i] = itime[i];
+        id_.itimestep[i] = itimestep[i];
+        for (int k = 0; k < 3; k++) {
+            id_.old_acc[i][k] = old_acc[3 * i + k];
+            id_.old_jerk[i][k] = old_jerk[3 * i + k];
+            id_.iacc[i][k] = iacc[3 * i + k];
+            id_.ijerk[i][k] = ijerk[3 * i + k];
+            id_.ipos[i][k] = ipos[3 * i + k];
+            id_.ivel[i][k] = ivel[3 * i + k];
+        }
+    }
+    id_.correct(tnext);
+    for (int i = 0; i < ni; i++) {
+        itime[i] = id_.itime[i];
+        itimestep[i] = id_.itimestep[i];
+        for (int k = 0; k < 3; k++) {
+            ipos[3 * i + k] = id_.ipos[i][k];
+            ivel[3 * i + k] = id_.ivel[i][k];
+        }
+    }
+    return 0;
+}
+
 // Run the reference Hermite integrator to t_end (the loop of
 // src/amuse_ph4/interface.cc:673-674 / parallel_hermite_4.cc run_hermite4).
 // use_gpu selects the g6 ABI path when compiled -DGPU.

@@ -235,6 +235,33 @@ def test_block_step_sequence_across_latency_path_thresholds(g6):
                            address=sel.astype(np.int32))
 
 
+def test_bhtree_interaction_list_call_pattern(g6):
+    """The third g6 caller, src/amuse_bhtree/src/BHtree.C:763-885: every tree walk
+    re-sends its whole interaction list (address = index = position in the list, velocities zero,
+    t = 0), then asks for the forces on the leaf's particles -- which are members of the list, so the
+    self pair is excluded by id -- with nj = list length (shrinking and growing from call to call),
+    h2 = 0 and plain lasthalf."""
+    O = _O()
+    rnd = np.random.RandomState(21)
+    g6.nj = 0
+    g6.set_variant(0)
+    z = np.zeros(3)
+    for length, ni in ((3000, 64), (700, 300), (5000, 17), (260, 260)):
+        pos = rnd.standard_normal((length, 3))
+        mass = rnd.uniform(0.5, 1.5, length) / length
+        first_leaf = int(rnd.randint(0, length - ni + 1))
+        g6.set_ti(0.0)
+        for i in range(length):
+            g6.set_j_particle(i, i, 0.0, 0.0, mass[i], z, z, z, z, pos[i])
+        idx = np.arange(first_leaf, first_leaf + ni, dtype=np.int32)
+        vel0 = np.zeros((ni, 3))
+        out = g6.calc(idx, pos[idx], vel0, 1e-4, nj=length, want_nn=False)
+        ref = O.force(pos[idx], vel0, mass, pos, np.zeros_like(pos), 1e-4, iid=idx, jid=np.arange(length, dtype=np.int32))
+        assert rel_vec_err(out["acc"], ref["acc"]).max() <= TOL, (length, ni)
+        assert rel_err(out["pot"], ref["pot"]).max() <= TOL, (length, ni)
+        assert np.abs(out["jerk"]).max() == 0.0          # all velocities are zero
+
+
 def test_neighbour_lists(g6):
     O = _O()
     m, x, v = P.new_plummer_model(3000, seed=8)
