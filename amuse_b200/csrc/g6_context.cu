@@ -485,6 +485,7 @@ int choose_variant(int ni, int nj)
     const int cand[3] = {V_T1, V_W1, V_P2W};
     const double pair_cost[3] = {1.0, 1.0, 0.95};  // measured: in this latency-bound regime packed pairs buy little
     const double fixed = 64.0;                     // prologue + TMA latency + reduction, in pair units
+    const double per_tile = 6.0;                   // barrier wait, FP64 flush, next TMA issue: paid per tile by every CTA
     const int ntiles = std::max(1, (nj + TILE - 1) / TILE);
     int best = V_P2W;
     double best_cost = 1e300;
@@ -495,7 +496,7 @@ int choose_variant(int ni, int nj)
         const long long cta_tiles = (long long)ntiles * nib;
         const double waves_min = std::max(1.0, (double)cta_tiles / slots);   // tiles each slot must take
         const double tps = std::ceil(waves_min);
-        const double cost = tps * vi.ib * pair_cost[c] + fixed * std::max(1.0, (double)nib / slots);
+        const double cost = tps * (vi.ib * pair_cost[c] + per_tile) + fixed * std::max(1.0, (double)nib / slots);
         if (cost < best_cost) {
             best_cost = cost;
             best = cand[c];
@@ -693,6 +694,9 @@ void stage_j(int address, int index, double tj, double mass, const double *j6, c
     u.addr = address;
     u.pad[0] = u.pad[1] = u.pad[2] = 0;
     if (address + 1 > G.nj_hi) G.nj_hi = address + 1;
+    // big batches (the caller is sending back a large block, or loading the system) go out while the
+    // caller is still staging the rest, so the next force call does not start with a multi-MB upload
+    if (G.up_n >= 8192) flush_updates();
 }
 
 // Chunk size of the device path: unlike the ABI path it is not tied to g6_npipes().  A launch of the
@@ -1606,6 +1610,23 @@ double g6x_time_predictor(int nj, int reps)
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     return (double)ms / reps;
+}
+
+double g6x_latency_probe(int kernels, int reps)
+{
+    require_open("g6x_latency_probe");
+    CK(cudaStreamSynchronize(G.stream));
+    volatile unsigned long long *flag = G.h_flag;
+    double t0 = 0;
+    for (int r = 0; r < reps + 20; r++) {
+        if (r == 20) t0 = wall();
+        const unsigned long long seq = ++G.flag_seq;
+        for (int k = 0; k < kernels - 1; k++) latency_probe_kernel<<<1, 32, 0, G.stream>>>(nullptr, 0, G.d_done + 0);
+        latency_probe_kernel<<<1, 32, 0, G.stream>>>(G.dev_h_flag, seq, nullptr);
+        while (*flag != seq) {
+        }
+    }
+    return 1e6 * (wall() - t0) / reps;
 }
 
 int g6x_set_variant(int variant)

@@ -1513,6 +1513,17 @@ __global__ void __launch_bounds__(256) peer_combine_kernel(const PeerSlots ps, c
     }
 }
 
+// Launch-latency probe: the floor of "launch k dependent kernels, the last one raises a flag in mapped host
+// memory, the host spins on it" -- what one block step of the latency path can cost at best.
+__global__ void latency_probe_kernel(unsigned long long *host_flag, unsigned long long seq, unsigned int *sink)
+{
+    if (sink && threadIdx.x == 1234567) *sink = 1;
+    if (host_flag && threadIdx.x == 0) {
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned long long *>(host_flag) = seq;
+    }
+}
+
 // ---------------------------------------------------------------------------
 // FP32 pipe microbenchmark (roofline denominator measured on the device).
 // ---------------------------------------------------------------------------

@@ -231,6 +231,9 @@ int g6x_read_predicted(int nj, double (*pos)[3], double (*vel)[3]);
 /* Time only the j-predictor / j-update kernels (CUDA events, ms per launch,
  * averaged over reps) for the HBM roofline of those kernels. */
 double g6x_time_predictor(int nj, int reps);
+/* Floor of the latency path: microseconds per round trip of `kernels` dependent empty launches
+ * whose last one raises the completion flag in mapped host memory (mean over reps). */
+double g6x_latency_probe(int kernels, int reps);
 /* Which force-kernel variant the next calls use: 0 = auto, else a fixed variant
  * id; for benchmarking and tests. */
 int g6x_set_variant(int variant);
