@@ -119,6 +119,7 @@ struct Context {
     int direct_max = 2048;             // i-blocks up to this size get their results by direct host writes
     int inline_max = 384;              // ... and up to this size travel in the kernel parameters
     int fuse = 1;                      // scatter+predict fused into one launch for small update batches
+    int eager_flush = 8192;            // staged updates that trigger an upload while the caller is still staging
     int zc_up_max = 512;               // j-update batches up to this size are read zero-copy by scatter_kernel
     double *dev_h_sum = nullptr;       // device alias of h_sum
     JUpdate *dev_h_up2[2] = {nullptr, nullptr};   // device aliases of h_up2[]
@@ -696,7 +697,7 @@ void stage_j(int address, int index, double tj, double mass, const double *j6, c
     if (address + 1 > G.nj_hi) G.nj_hi = address + 1;
     // big batches (the caller is sending back a large block, or loading the system) go out while the
     // caller is still staging the rest, so the next force call does not start with a multi-MB upload
-    if (G.up_n >= 8192) flush_updates();
+    if (G.eager_flush > 0 && G.up_n >= G.eager_flush) flush_updates();
 }
 
 // Chunk size of the device path: unlike the ABI path it is not tied to g6_npipes().  A launch of the
@@ -787,6 +788,7 @@ int g6_open_(int *id)
     G.inline_max = std::min(384, std::max(0, env_int("G6_B200_INLINE_MAX", 384)));
     G.zc_up_max = std::max(0, env_int("G6_B200_ZC_UPDATES", 512));
     G.fuse = env_int("G6_B200_FUSE", 1);
+    G.eager_flush = env_int("G6_B200_EAGER_FLUSH", 8192);
     G.trace = env_int("G6_B200_TRACE", 0);
     for (double &t : G.tr) t = 0;
     G.tr_calls = 0;
@@ -1435,19 +1437,16 @@ int g6x_hermite_step(int nj, int ni, const int *ilist, double tnext, double eta,
     Context::Hermite &H = G.herm;
     if (G.pending) CK(cudaStreamSynchronize(G.stream));
     flush_updates();
-    const int chunk = G.npipes;
-    hermite_reserve(std::min(ni, chunk));
-    // every chunk reads the state the previous chunk already corrected, exactly like ph4 would if it
-    // split a block (it does not: blocks above npipes only occur in synchronised (re)starts)
-    for (int i0 = 0; i0 < ni; i0 += chunk) {
-        const int n = std::min(chunk, ni - i0);
-        memcpy(H.h_ilist, ilist + i0, sizeof(int) * n);
-        memcpy(H.h_olddt, old_dt + i0, sizeof(double) * n);
-        hermite_pass(nj, n, tnext, eta, eps2, 0);
-        memcpy(new_dt + i0, H.h_outdt, sizeof(double) * n);
-        if (pot) memcpy(pot + i0, H.h_outpot, sizeof(double) * n);
-        if (nn) memcpy(nn + i0, H.h_outnn, sizeof(int) * n);
-    }
+    if (ni <= 0) return 0;
+    // the whole block in one pass, whatever its size: every force is computed against the PREDICTED state
+    // of all j before any particle is corrected, as in idata::advance
+    hermite_reserve(ni);
+    memcpy(H.h_ilist, ilist, sizeof(int) * ni);
+    memcpy(H.h_olddt, old_dt, sizeof(double) * ni);
+    hermite_pass(nj, ni, tnext, eta, eps2, 0);
+    memcpy(new_dt, H.h_outdt, sizeof(double) * ni);
+    if (pot) memcpy(pot, H.h_outpot, sizeof(double) * ni);
+    if (nn) memcpy(nn, H.h_outnn, sizeof(int) * ni);
     return 0;
 }
 
@@ -1458,18 +1457,13 @@ int g6x_hermite_init(int nj, double t0, double eta, double eps2, double *timeste
     if (G.pending) CK(cudaStreamSynchronize(G.stream));
     flush_updates();
     nj = std::min(nj, G.capacity);
-    const int chunk = G.npipes;
-    hermite_reserve(std::min(nj, chunk));
+    if (nj <= 0) return -1;
+    hermite_reserve(nj);
     H.time.assign(nj, t0);
     H.dt.assign(nj, 0.0);
-    // forces of all particles at t0 against the state as it is; acc/jerk only enter the predictor for
-    // dt != 0, and all particles sit at t0, so writing them chunk by chunk does not change later chunks
-    for (int i0 = 0; i0 < nj; i0 += chunk) {
-        const int n = std::min(chunk, nj - i0);
-        for (int k = 0; k < n; k++) H.h_ilist[k] = i0 + k;
-        hermite_pass(nj, n, t0, eta, eps2, 1);
-        memcpy(H.dt.data() + i0, H.h_outdt, sizeof(double) * n);
-    }
+    for (int k = 0; k < nj; k++) H.h_ilist[k] = k;
+    hermite_pass(nj, nj, t0, eta, eps2, 1);   // forces of all particles at t0, first steps (jdata.cc:503-548)
+    memcpy(H.dt.data(), H.h_outdt, sizeof(double) * nj);
     if (timestep_out) memcpy(timestep_out, H.dt.data(), sizeof(double) * nj);
     H.system_time = t0;
     H.block_steps = H.particle_steps = 0;

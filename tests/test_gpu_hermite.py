@@ -82,6 +82,34 @@ def test_init_and_block_steps_match_oracle(g6):
         dt[ilist] = new_dt
 
 
+def test_blocks_larger_than_npipes_go_in_one_pass(g6):
+    """A synchronised (re)start makes every particle active: the block exceeds g6_npipes() and must still see
+    only PREDICTED j (no particle corrected before all forces are in), like idata::advance."""
+    O = _O()
+    n, eta, eps2 = 20000, 0.14, 1e-4
+    assert n > g6.npipes
+    m, x, v, ids = _load(g6, n, 8)
+    dt = np.zeros(n)
+    g6.L.g6x_hermite_init(n, 0.0, eta, eps2, dt.ctypes.data)
+    t, sx, sv, sa, sj = _state(g6, n)
+    samp = np.arange(0, n, 97)
+    ref = O.force(x[samp], v[samp], m, x, v, eps2, iid=ids[samp], jid=ids, scales=True)
+    check_forces(dict(acc=sa[samp], jerk=sj[samp], pot=ref["pot"]), ref, what="init forces, n > npipes")
+    assert np.mean(dt == O.initial_timestep(0.0, eta, sa, sj)) > 0.999
+    # force every particle to step together to t = 2^-12 (all steps are powers of two >= that? use the smallest)
+    tnext = float(dt.min())
+    ilist = np.arange(n, dtype=np.int32)
+    new_dt = np.zeros(n)
+    g6.L.g6x_hermite_step(n, n, ilist, tnext, eta, eps2, dt, new_dt, None, None)
+    after = _state(g6, n)
+    pp, pv = O.predict(tnext, t, sx, sv, sa, sj)
+    f = O.force(pp[samp], pv[samp], m, pp, pv, eps2, iid=ids[samp], jid=ids, scales=True)
+    check_forces(dict(acc=after[3][samp], jerk=after[4][samp], pot=f["pot"]), f, what="all-particle block")
+    cp, cv, ct, cdt = O.correct(tnext, eta, t, dt, sa, sj, after[3], after[4], pp, pv)
+    assert np.abs(after[1] - cp).max() <= 1e-14 * np.abs(cp).max()
+    assert np.array_equal(new_dt, cdt)
+
+
 def test_evolve_tracks_ph4_cpu_mode(g6):
     O = _O()
     if not O.ref_available():

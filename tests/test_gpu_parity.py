@@ -262,6 +262,24 @@ def test_bhtree_interaction_list_call_pattern(g6):
         assert np.abs(out["jerk"]).max() == 0.0          # all velocities are zero
 
 
+def test_big_update_batches_flush_early_and_last_write_still_wins(g6):
+    """Batches of >= 8192 staged updates go out while the caller is still staging (stage_j); a particle written
+    before and after such a flush must end up with its last value (sapporo.cpp:83-110 semantics across batches)."""
+    O = _O()
+    n = 20000
+    m, x, v = P.new_plummer_model(n, seed=14)
+    ids = np.arange(1, n + 1, dtype=np.int32)
+    _fresh(g6, ids, m, x + 3.0, v)                       # wrong positions everywhere ...
+    z = np.zeros(3)
+    for j in (0, 5000, 8191, 8192, 19999):               # ... and again, one by one, around the flush boundary
+        g6.set_j_particle(j, int(ids[j]), 0.0, 0.125, m[j], z, z, z, v[j], x[j] - 1.0)
+    g6.set_j_particles(ids, m, x, v)                     # the right values: 20000 records = two early flushes + a rest
+    out = g6.calc(ids[:300], x[:300], v[:300], 1e-4)
+    ref = O.force(x[:300], v[:300], m, x, v, 1e-4, iid=ids[:300], jid=ids, scales=True)
+    check_forces(out, ref, what="early flush")
+    check_nn(out["nn"], ref["nn"], ids, x[:300], x)
+
+
 def test_neighbour_lists(g6):
     O = _O()
     m, x, v = P.new_plummer_model(3000, seed=8)
