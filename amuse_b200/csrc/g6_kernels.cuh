@@ -953,7 +953,10 @@ __device__ __forceinline__ void pair_geometry(const float4 a, const float4 b, co
 }
 
 // One j against an i-pair, no masks: 38 packed FP32 operations + 2 MUFU.  Accumulates -acc, -jerk, +pot.
-template <bool NR>
+// EPS0: the caller runs unsoftened (eps2 = 0, ph4's AMUSE default).  The reference still adds 2^-52 to r2
+// (idata.cc:216); in FP32 that add is the identity for r2 > 2^-26, so it is skipped here and the group
+// verification (running minimum of r2) redoes any group that holds a closer pair with the exact path.
+template <bool NR, bool EPS0>
 __device__ __forceinline__ u64 interact2_fast(const float4 a, const float4 b, const float4 c, const IPair &I,
                                               const u64 eps2p, Acc7P &s)
 {
@@ -963,7 +966,7 @@ __device__ __forceinline__ u64 interact2_fast(const float4 a, const float4 b, co
     const u64 dvy = add2(pk(c.y, c.y), I.nvy);
     const u64 dvz = add2(pk(c.z, c.z), I.nvz);
     const u64 xv = fma2(dz, dvz, fma2(dy, dvy, mul2(dx, dvx)));
-    const u64 r2e = add2(r2, eps2p);
+    const u64 r2e = EPS0 ? r2 : add2(r2, eps2p);
     float e0, e1;
     upk(r2e, e0, e1);
     const u64 y0 = pk(rsqrt_approx(e0), rsqrt_approx(e1));
@@ -996,9 +999,12 @@ __device__ __forceinline__ u64 interact2_fast(const float4 a, const float4 b, co
     return r2;
 }
 
-template <int IPT, bool NN, bool NR, int MINB>
+template <int IPT, bool NN, bool NR, int MINB, bool EPS0>
 __global__ void __launch_bounds__(THREADS, MINB) force_fast_kernel(const ForceArgs p)
 {
+    // a pair this close sends its group down the exact path (coincident pairs; with EPS0 also pairs for
+    // which r2 + 2^-52 is not r2 in FP32)
+    constexpr float R2_EXACT = EPS0 ? 1.4901161193847656e-08f /* 2^-26 */ : TINYF;
     constexpr bool DUAL = (G6_DUAL != 0) && (IPT >= G6_DUAL);
     static_assert(IPT % 2 == 0, "i-particles are processed in packed pairs");
     static_assert(TILE % GRP == 0 && GRP % (2 * G6_FUNROLL) == 0, "group shape");
@@ -1059,7 +1065,7 @@ __global__ void __launch_bounds__(THREADS, MINB) force_fast_kernel(const ForceAr
     }
 
     double D[IPT][7];
-    float rmin[IPT], rprev[IPT];   // running minimum of r2 (masked rule), and its value at the last group boundary
+    float rmin[IPT], rprev[IPT];   // minimum of r2 over the current group; running minimum (masked rule) before it
     int jgrp[IPT];                 // first j of the group that last lowered it (local address), -1: none
 #pragma unroll
     for (int k = 0; k < IPT; k++) {
@@ -1091,6 +1097,8 @@ __global__ void __launch_bounds__(THREADS, MINB) force_fast_kernel(const ForceAr
         for (int jj0 = 0; jj0 < cnt; jj0 += GRP) {
             Acc7P S[NP];
             bool fast = !tile_masked;
+#pragma unroll
+            for (int k = 0; k < IPT; k++) rmin[k] = __int_as_float(0x7f800000);
             if (fast) {
                 // DUAL: even and odd j of the group go to separate FP32 partial sums (each spans GRP/2
                 // pairs, which is what bounds the rounding error of a sum dominated by one close pair)
@@ -1107,8 +1115,8 @@ __global__ void __launch_bounds__(THREADS, MINB) force_fast_kernel(const ForceAr
                     const float4 a1 = tA[jj + 1], b1 = tB[jj + 1], c1 = tC[jj + 1];
 #pragma unroll
                     for (int q = 0; q < NP; q++) {
-                        const u64 ra = interact2_fast<NR>(a0, b0, c0, IP[q], eps2p, S[q]);
-                        const u64 rb = interact2_fast<NR>(a1, b1, c1, IP[q], eps2p, DUAL ? S1[q] : S[q]);
+                        const u64 ra = interact2_fast<NR, EPS0>(a0, b0, c0, IP[q], eps2p, S[q]);
+                        const u64 rb = interact2_fast<NR, EPS0>(a1, b1, c1, IP[q], eps2p, DUAL ? S1[q] : S[q]);
                         float ra0, ra1, rb0, rb1;
                         upk(ra, ra0, ra1);
                         upk(rb, rb0, rb1);
@@ -1127,11 +1135,11 @@ __global__ void __launch_bounds__(THREADS, MINB) force_fast_kernel(const ForceAr
                 }
                 bool bad = false;
 #pragma unroll
-                for (int k = 0; k < IPT; k++) bad |= !(rmin[k] > TINYF);
-                if (__any_sync(0xffffffffu, bad)) {   // a coincident pair: redo the group with the masks
+                for (int k = 0; k < IPT; k++) bad |= !(rmin[k] > R2_EXACT);
+                if (__any_sync(0xffffffffu, bad)) {   // a pair too close for the fast path: redo the group exactly
                     fast = false;
 #pragma unroll
-                    for (int k = 0; k < IPT; k++) rmin[k] = rprev[k];
+                    for (int k = 0; k < IPT; k++) rmin[k] = __int_as_float(0x7f800000);
                 }
             }
             if (!fast) {
@@ -1162,12 +1170,11 @@ __global__ void __launch_bounds__(THREADS, MINB) force_fast_kernel(const ForceAr
             if (NN) {
 #pragma unroll
                 for (int k = 0; k < IPT; k++) {
-                    if (rmin[k] < rprev[k]) jgrp[k] = jtile + jj0;
-                    rprev[k] = rmin[k];
+                    if (rmin[k] < rprev[k]) {   // strict: the first group that reaches the minimum keeps it
+                        jgrp[k] = jtile + jj0;
+                        rprev[k] = rmin[k];
+                    }
                 }
-            } else {
-#pragma unroll
-                for (int k = 0; k < IPT; k++) rprev[k] = rmin[k];
             }
         }
 
@@ -1186,7 +1193,7 @@ __global__ void __launch_bounds__(THREADS, MINB) force_fast_kernel(const ForceAr
 #pragma unroll
     for (int k = 0; k < IPT; k++) {
         int jm = -1;
-        if (NN && jgrp[k] >= 0 && rmin[k] < 1.0e30f) {   // >= 1e30: only parked (massless) slots were seen
+        if (NN && jgrp[k] >= 0 && rprev[k] < 1.0e30f) {   // >= 1e30: only parked (massless) slots were seen
             const int jend = (jgrp[k] + GRP < p.nj) ? jgrp[k] + GRP : p.nj;
             for (int jj = jgrp[k]; jj < jend; jj++) {
                 const float4 a = p.jA[jj], b = p.jB[jj];
@@ -1195,13 +1202,13 @@ __global__ void __launch_bounds__(THREADS, MINB) force_fast_kernel(const ForceAr
                 float r0, r1;
                 upk(r2, r0, r1);
                 const float r = (k & 1) ? r1 : r0;
-                if (__float_as_int(b.w) != iid[k] && r > TINYF && r == rmin[k]) {
+                if (__float_as_int(b.w) != iid[k] && r > TINYF && r == rprev[k]) {
                     jm = jj;
                     break;
                 }
             }
         }
-        key[k] = (jm >= 0) ? make_key(rmin[k], jm + p.j_offset) : KEY_NONE;
+        key[k] = (jm >= 0) ? make_key(rprev[k], jm + p.j_offset) : KEY_NONE;
     }
 
     // ---- totals -> global (final or per-split partial) -----------------------------------
