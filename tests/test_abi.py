@@ -74,3 +74,23 @@ def test_open_fails_loudly_without_gpu(built_lib):
             "i=ctypes.c_int(0); L.g6_open_(ctypes.byref(i)); print('SURVIVED')" % ROOT)
     r = subprocess.run(["python", "-c", code], capture_output=True, text=True)
     assert r.returncode != 0 and "SURVIVED" not in r.stdout and "no CUDA device" in r.stderr
+
+
+def test_install_lays_out_what_amuse_configure_looks_for(built_lib, tmp_path):
+    """lib/sapporo_light/Makefile:28-101 + support/shared/m4/amuse_lib.m4:17-72: libraries under lib/, the
+    header under include/ (also as g6lib.h), and the sapporo_light / g6lib pkg-config modules."""
+    import subprocess
+    prefix = str(tmp_path / "prefix")
+    csrc = os.path.join(ROOT, "amuse_b200", "csrc")
+    subprocess.check_call(["make", "-s", "-C", csrc, "install", "PREFIX=" + prefix])
+    for rel in ("lib/libsapporo.so", "lib/libg6.so", "include/g6_b200.h", "include/g6lib.h",
+                "lib/pkgconfig/sapporo_light.pc", "lib/pkgconfig/g6lib.pc"):
+        assert os.path.exists(os.path.join(prefix, rel)), rel
+    pc = open(os.path.join(prefix, "lib/pkgconfig/sapporo_light.pc")).read()
+    assert "Name: sapporo_light" in pc and "-lsapporo" in pc and ("prefix=" + prefix) in pc
+    pc = open(os.path.join(prefix, "lib/pkgconfig/g6lib.pc")).read()
+    assert "Name: g6lib" in pc and "-lg6" in pc
+    lib = ctypes.CDLL(os.path.join(prefix, "lib", "libg6.so"))
+    assert lib.g6_npipes_() == 16384
+    subprocess.check_call(["make", "-s", "-C", csrc, "uninstall", "PREFIX=" + prefix])
+    assert not os.path.exists(os.path.join(prefix, "lib/libsapporo.so"))
