@@ -144,6 +144,7 @@ struct Context {
         unsigned int *h_err = nullptr, *dev_h_err = nullptr;   // mapped: a combine kernel gave up waiting
     } peer;
     // mirrors of the launch being issued (set by g6x_calc_device_allreduce around launch_force)
+    int win_lo = 0;   // j-window offset of the launch being issued (sharded Hermite step), multiple of TILE
     int mir_n = 0;
     double *mir_sum[MAX_PEERS] = {};
     u64 *mir_key[MAX_PEERS] = {};
@@ -169,6 +170,10 @@ struct Context {
         double system_time = 0.0;
         long long block_steps = 0, particle_steps = 0;
         bool initialised = false;
+        // multi-GPU: the state is replicated on every rank, the FORCES are sharded -- this rank sums over
+        // the j-window [shard_lo, shard_hi) and the partials are exchanged over peer memory; every rank then
+        // applies the same corrector to its replica, so no state ever travels (g6x_hermite_set_shard)
+        int shard_lo = 0, shard_hi = 0;   // hi == 0: no sharding
     } herm;
 
     // captured by firsthalf
@@ -520,7 +525,7 @@ void launch_force(int nj, int ni, const float4 *iA, const float4 *iB, const floa
                   bool list, double *out_sum, u64 *out_key, int *out_nnid, const float4 *inline_src = nullptr,
                   unsigned long long flag_seq = 0, const HermiteArgs *herm = nullptr)
 {
-    if (nj > G.capacity) nj = G.capacity;
+    if (nj > G.capacity - G.win_lo) nj = G.capacity - G.win_lo;
     int v = choose_variant(ni, nj);
     if (herm && !(v == V_W1 || v == V_T1 || v == V_P2W)) {
         fprintf(stderr, "g6_b200: FATAL fused Hermite corrector with variant %d\n", v);
@@ -563,12 +568,14 @@ void launch_force(int nj, int ni, const float4 *iA, const float4 *iB, const floa
     nsplit = (ntiles + tps - 1) / tps;
 
     ForceArgs a{};
-    a.jA = G.js.A; a.jB = G.js.B; a.jC = G.js.C;
+    // G.win_lo > 0: the launch works on the j-window [win_lo, win_lo + nj) of the local arrays (sharded
+    // Hermite step on a replicated state); win_lo is a multiple of TILE, so tiles keep their id ranges
+    a.jA = G.js.A + G.win_lo; a.jB = G.js.B + G.win_lo; a.jC = G.js.C + G.win_lo;
     a.iA = iA; a.iB = iB; a.iC = iC;
     a.ni = ni; a.nj = nj;
     a.tiles_per_split = tps; a.nsplit = nsplit;
     a.ni_pad = ni;
-    a.j_offset = G.j_offset;
+    a.j_offset = G.j_offset + G.win_lo;
     // many splits of few i-blocks: sum the partials with a kernel of its own (one warp per i, spread
     // over the SMs) instead of the last CTA -- except for the 4-particle shape, whose last CTA puts
     // 32 lanes on each i
@@ -661,6 +668,7 @@ void free_all()
         H.cap = 0;
         H.time.clear(); H.dt.clear();
         H.initialised = false;
+        H.shard_lo = H.shard_hi = 0;
     }
     G.dev_h_sum = nullptr; G.dev_h_flag = nullptr; G.dev_h_up2[0] = G.dev_h_up2[1] = nullptr;
     G.cur_direct = false; G.i_on_device = false;
@@ -1162,6 +1170,72 @@ int g6x_predict(int nj, double ti)
     return 0;
 }
 
+// ---- peer exchange helpers (shared by g6x_calc_device_allreduce and the sharded Hermite step) ----
+struct ExchangeSlots {
+    unsigned char *half[MAX_PEERS + 1];   // slot of THIS rank in every rank's buffer, current half
+};
+static ExchangeSlots exchange_begin(int ni, const char *who)
+{
+    Context::Peer &P = G.peer;
+    if (!P.attached || ni > P.cap) {
+        fprintf(stderr, "g6_b200: FATAL %s: %s (ni %d, capacity %d)\n", who,
+                P.attached ? "i-set exceeds the exchange capacity" : "no peers attached", ni, P.cap);
+        exit(-1);
+    }
+    P.seq++;
+    ExchangeSlots e{};
+    for (int r = 0; r < P.world; r++) e.half[r] = P.peer_buf[r] + (P.seq & 1) * P.half_bytes + P.rank * P.slot_bytes;
+    return e;
+}
+static double *slot_sum(unsigned char *b, int i0) { return reinterpret_cast<double *>(b) + 7 * (size_t)i0; }
+static u64 *slot_key(unsigned char *b, int i0)
+{
+    return reinterpret_cast<u64 *>(b + sizeof(double) * 7 * (size_t)G.peer.cap) + i0;
+}
+static int *slot_id(unsigned char *b, int i0)
+{
+    return reinterpret_cast<int *>(b + sizeof(double) * 8 * (size_t)G.peer.cap) + i0;
+}
+static void exchange_set_mirrors(const ExchangeSlots &e, int i0)
+{
+    Context::Peer &P = G.peer;
+    G.mir_n = 0;
+    for (int r = 0; r < P.world; r++) {
+        if (r == P.rank) continue;
+        G.mir_sum[G.mir_n] = slot_sum(e.half[r], i0);
+        G.mir_key[G.mir_n] = slot_key(e.half[r], i0);
+        G.mir_id[G.mir_n] = slot_id(e.half[r], i0);
+        G.mir_n++;
+    }
+}
+static void exchange_finish(int ni, double *d_sum, unsigned long long *d_key, int *d_nnid)
+{
+    Context::Peer &P = G.peer;
+    PeerSlots ps{};
+    ps.world = P.world;
+    ps.rank = P.rank;
+    unsigned char *mine = P.buf + (P.seq & 1) * P.half_bytes;
+    for (int r = 0; r < P.world; r++) {
+        unsigned char *b = mine + r * P.slot_bytes;
+        ps.sum[r] = reinterpret_cast<const double *>(b);
+        ps.key[r] = reinterpret_cast<const u64 *>(b + sizeof(double) * 7 * (size_t)P.cap);
+        ps.id[r] = reinterpret_cast<const int *>(b + sizeof(double) * 8 * (size_t)P.cap);
+    }
+    const size_t foff = P.flags_off + (P.seq & 1) * sizeof(unsigned long long) * P.world;
+    ps.flag = reinterpret_cast<volatile unsigned long long *>(P.buf + foff);
+    ps.n_remote = 0;
+    for (int r = 0; r < P.world; r++)
+        if (r != P.rank)
+            ps.remote_flag[ps.n_remote++] = reinterpret_cast<unsigned long long *>(P.peer_buf[r] + foff) + P.rank;
+    peer_flag_kernel<<<1, 32, 0, G.stream>>>(ps, P.seq);
+    CK(cudaGetLastError());
+    const int ctas = std::max(1, std::min(2 * G.sm_count, (ni + 255) / 256));
+    peer_combine_kernel<<<ctas, 256, 0, G.stream>>>(ps, P.seq, ni, d_sum, reinterpret_cast<u64 *>(d_key), d_nnid,
+                                                    P.dev_h_err);
+    CK(cudaGetLastError());
+    G.launches += 2;
+}
+
 // Shared body of the device-resident entry points.  With peers attached and `exchange` set, every launch
 // writes this rank's partials into its slot of all exchange buffers (own + peers, over NVLink) and the
 // call ends with the flag + combine kernels, so d_sum/d_key/d_nnid hold the totals over all j-shards.
@@ -1177,16 +1251,8 @@ static int calc_device_impl(int nj, int ni, const int *d_index, const double *d_
         exit(-1);
     }
     Context::Peer &P = G.peer;
-    unsigned char *half[MAX_PEERS + 1] = {};
-    if (exchange) {
-        if (!P.attached || ni > P.cap) {
-            fprintf(stderr, "g6_b200: FATAL g6x_calc_device_allreduce: %s (ni %d, capacity %d)\n",
-                    P.attached ? "i-set exceeds the exchange capacity" : "no peers attached", ni, P.cap);
-            exit(-1);
-        }
-        P.seq++;
-        for (int r = 0; r < P.world; r++) half[r] = P.peer_buf[r] + (P.seq & 1) * P.half_bytes + P.rank * P.slot_bytes;
-    }
+    ExchangeSlots ex{};
+    if (exchange) ex = exchange_begin(ni, "g6x_calc_device_allreduce");
     const int chunk = device_chunk(ni, std::min(nj, G.capacity));
     if (chunk > G.i2_cap) {
         CK(cudaStreamSynchronize(G.stream));
@@ -1206,45 +1272,12 @@ static int calc_device_impl(int nj, int ni, const int *d_index, const double *d_
             launch_force(nj, n, A, B, C, (float)eps2, nn, false, d_sum + 7 * (size_t)i0, d_key + i0, d_nnid + i0);
             continue;
         }
-        // slot layout: sum[cap][7] | key[cap] | id[cap]
-        auto s_sum = [&](unsigned char *b) { return reinterpret_cast<double *>(b) + 7 * (size_t)i0; };
-        auto s_key = [&](unsigned char *b) { return reinterpret_cast<u64 *>(b + sizeof(double) * 7 * (size_t)P.cap) + i0; };
-        auto s_id = [&](unsigned char *b) { return reinterpret_cast<int *>(b + sizeof(double) * 8 * (size_t)P.cap) + i0; };
-        G.mir_n = 0;
-        for (int r = 0; r < P.world; r++) {
-            if (r == P.rank) continue;
-            G.mir_sum[G.mir_n] = s_sum(half[r]);
-            G.mir_key[G.mir_n] = s_key(half[r]);
-            G.mir_id[G.mir_n] = s_id(half[r]);
-            G.mir_n++;
-        }
-        launch_force(nj, n, A, B, C, (float)eps2, nn, false, s_sum(half[P.rank]), s_key(half[P.rank]), s_id(half[P.rank]));
+        exchange_set_mirrors(ex, i0);
+        unsigned char *own = ex.half[P.rank];
+        launch_force(nj, n, A, B, C, (float)eps2, nn, false, slot_sum(own, i0), slot_key(own, i0), slot_id(own, i0));
         G.mir_n = 0;
     }
-    if (exchange && ni > 0) {
-        PeerSlots ps{};
-        ps.world = P.world;
-        ps.rank = P.rank;
-        unsigned char *mine = P.buf + (P.seq & 1) * P.half_bytes;
-        for (int r = 0; r < P.world; r++) {
-            unsigned char *b = mine + r * P.slot_bytes;
-            ps.sum[r] = reinterpret_cast<const double *>(b);
-            ps.key[r] = reinterpret_cast<const u64 *>(b + sizeof(double) * 7 * (size_t)P.cap);
-            ps.id[r] = reinterpret_cast<const int *>(b + sizeof(double) * 8 * (size_t)P.cap);
-        }
-        const size_t foff = P.flags_off + (P.seq & 1) * sizeof(unsigned long long) * P.world;
-        ps.flag = reinterpret_cast<volatile unsigned long long *>(P.buf + foff);
-        ps.n_remote = 0;
-        for (int r = 0; r < P.world; r++)
-            if (r != P.rank)
-                ps.remote_flag[ps.n_remote++] = reinterpret_cast<unsigned long long *>(P.peer_buf[r] + foff) + P.rank;
-        peer_flag_kernel<<<1, 32, 0, G.stream>>>(ps, P.seq);
-        CK(cudaGetLastError());
-        const int ctas = std::max(1, std::min(2 * G.sm_count, (ni + 255) / 256));
-        peer_combine_kernel<<<ctas, 256, 0, G.stream>>>(ps, P.seq, ni, d_sum, d_key, d_nnid, P.dev_h_err);
-        CK(cudaGetLastError());
-        G.launches += 2;
-    }
+    if (exchange && ni > 0) exchange_finish(ni, d_sum, d_key, d_nnid);
     return 0;
 }
 
@@ -1396,7 +1429,33 @@ static void hermite_pass(int nj, int n, double tnext, double eta, double eps2, i
     h.flag_seq = ++G.flag_seq;
     const int ctas = (n + 255) / 256;
     G.ti = tnext;
-    if (n <= 384 && G.variant == V_AUTO) {
+    if (H.shard_hi > 0) {
+        // replicated state, sharded forces: gather the block (every rank, identical), predict only this
+        // rank's j-window, sum over it with the partials mirrored into the peers' exchange buffers, combine,
+        // and let every rank correct its own replica with the identical totals
+        const int lo = H.shard_lo, hi = std::min(H.shard_hi, std::min(nj, G.capacity));
+        hermite_gather_kernel<<<ctas, 256, 0, G.stream>>>(h);
+        CK(cudaGetLastError());
+        if (hi > lo) {
+            const int tile0 = lo / TILE, ntiles = (hi - lo + TILE - 1) / TILE;
+            const int npred = std::max(std::min(nj, G.capacity), std::min(G.nj_hi, G.capacity));
+            predict_kernel<<<ntiles, TILE, 0, G.stream>>>(std::min(npred, hi), tnext, G.js, tile0);
+            CK(cudaGetLastError());
+        }
+        ExchangeSlots ex = exchange_begin(n, "g6x_hermite_step (sharded)");
+        exchange_set_mirrors(ex, 0);
+        unsigned char *own = ex.half[G.peer.rank];
+        G.win_lo = lo;
+        launch_force(std::max(0, hi - lo), n, h.iA, h.iB, h.iC, (float)eps2, true, false, slot_sum(own, 0),
+                     slot_key(own, 0), slot_id(own, 0));
+        G.win_lo = 0;
+        G.mir_n = 0;
+        exchange_finish(n, H.d_sum, reinterpret_cast<unsigned long long *>(H.d_key), H.d_nnid);
+        hermite_correct_kernel<<<ctas, 256, 0, G.stream>>>(h);
+        CK(cudaGetLastError());
+        G.launches += 3;
+        G.predicted_nj = -1;   // only a window was predicted
+    } else if (n <= 384 && G.variant == V_AUTO) {
         // small block: two launches -- (predict all j + gather/predict the block), then the force kernel
         // whose final-output stage is the corrector
         const int njc = std::min(nj, G.capacity);
@@ -1453,6 +1512,18 @@ int g6x_hermite_step(int nj, int ni, const int *ilist, double tnext, double eta,
     memcpy(new_dt, H.h_outdt, sizeof(double) * ni);
     if (pot) memcpy(pot, H.h_outpot, sizeof(double) * ni);
     if (nn) memcpy(nn, H.h_outnn, sizeof(int) * ni);
+    return 0;
+}
+
+int g6x_hermite_set_shard(int j_lo, int j_hi)
+{
+    require_open("g6x_hermite_set_shard");
+    if (j_hi > 0 && (j_lo < 0 || j_lo % TILE != 0 || j_hi < j_lo)) {
+        fprintf(stderr, "g6_b200: g6x_hermite_set_shard: j_lo must be a multiple of %d and <= j_hi\n", TILE);
+        return -1;
+    }
+    G.herm.shard_lo = j_hi > 0 ? j_lo : 0;
+    G.herm.shard_hi = j_hi > 0 ? j_hi : 0;
     return 0;
 }
 

@@ -160,10 +160,10 @@ __device__ __forceinline__ void apply_updates(const InlineU &iu, const JUpdate *
     __syncthreads();   // the block's own global writes are visible to its threads after the barrier
 }
 
-__global__ void __launch_bounds__(TILE) predict_kernel(int n, double ti, JState s)
+__global__ void __launch_bounds__(TILE) predict_kernel(int n, double ti, JState s, int tile0 = 0)
 {
     __shared__ int sh_lo[TILE / 32], sh_hi[TILE / 32];
-    predict_tile(blockIdx.x, n, ti, s, sh_lo, sh_hi);
+    predict_tile(tile0 + blockIdx.x, n, ti, s, sh_lo, sh_hi);
 }
 
 // scatter + predict in one launch (small update batches).

@@ -30,7 +30,7 @@ G6_SYMBOLS = [
     "g6x_calc_device", "g6x_device_chunk", "g6x_resolve_nn", "g6x_synchronize", "g6x_launch_count", "g6x_get_predicted",
     "g6x_read_predicted", "g6x_time_predictor", "g6x_set_variant", "g6x_fp32_peak",
     "g6x_peer_handle_bytes", "g6x_peer_alloc", "g6x_peer_attach", "g6x_peer_detach", "g6x_peer_error",
-    "g6x_calc_device_allreduce", "g6x_hermite_init", "g6x_hermite_step", "g6x_hermite_evolve", "g6x_hermite_get_state", "g6x_latency_probe",
+    "g6x_calc_device_allreduce", "g6x_hermite_init", "g6x_hermite_step", "g6x_hermite_evolve", "g6x_hermite_get_state", "g6x_hermite_set_shard", "g6x_latency_probe",
 ]
 
 _dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
@@ -78,6 +78,7 @@ def load():
     L.g6x_hermite_evolve.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, C.c_longlong, _dp]
     L.g6x_hermite_evolve.restype = C.c_longlong
     L.g6x_hermite_get_state.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.g6x_hermite_set_shard.argtypes = [C.c_int, C.c_int]
     L.g6x_latency_probe.argtypes = [C.c_int, C.c_int]
     L.g6x_latency_probe.restype = C.c_double
     L.g6x_device_chunk.argtypes = [C.c_int]

@@ -210,7 +210,13 @@ int g6x_resolve_nn(int ni, const unsigned long long *d_key, int rank,
  *                      max_block_steps (> 0); returns block steps done, stats[4] = time reached,
  *                      block steps, particle steps (both cumulative), wall seconds of this call.
  *   g6x_hermite_get_state : copy time/pos/vel/acc/jerk of the j-memory back (any pointer may be NULL).
- * Single j-shard only (the whole system on this device). */
+ * Multi-GPU (one process per GPU): every rank loads ALL particles (the state is replicated), attaches
+ * the peers (g6x_peer_*) and calls g6x_hermite_set_shard(j_lo, j_hi) with its window of the j-addresses
+ * (j_lo a multiple of 256; windows of all ranks tile [0, nj)).  A step then sums the forces over the
+ * window only, exchanges the partials over peer memory, and every rank corrects its replica with the
+ * identical totals -- no state and no host data ever travel; all ranks must make the same calls.
+ * j_hi <= 0 switches back to the single-device step. */
+int g6x_hermite_set_shard(int j_lo, int j_hi);
 int g6x_hermite_init(int nj, double t0, double eta, double eps2, double *timestep_out);
 int g6x_hermite_step(int nj, int ni, const int *ilist, double tnext, double eta,
                      double eps2, const double *old_dt, double *new_dt, double *pot,

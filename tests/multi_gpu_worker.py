@@ -91,9 +91,55 @@ def main():
             r[0][0, 0].item()      # the caller reads the result every step
         dt = (time.perf_counter() - t0) / 50
         msgs.append("block step ni=37 %s: %.1f us" % ("peer-memory exchange" if fused else "3 NCCL all-reduces", dt * 1e6))
+    g.close()
+
+    # ---- sharded device-resident Hermite integrator: replicated state, sharded forces ----------------
+    nh, eta, eps2, t_end = 4096, 0.14, 1e-4, 0.0625
+    mh, xh, vh = P.new_plummer_model(nh, seed=6)
+    idh = np.arange(1, nh + 1, dtype=np.int32)
+
+    def state(gg):
+        t = np.zeros(nh); x_ = np.zeros((nh, 3)); v_ = np.zeros((nh, 3)); a_ = np.zeros((nh, 3)); j_ = np.zeros((nh, 3))
+        gg.L.g6x_hermite_get_state(nh, t.ctypes.data, x_.ctypes.data, v_.ctypes.data, a_.ctypes.data, j_.ctypes.data)
+        return t, x_, v_, a_, j_
+
+    g = g6lib.G6(local)
+    L = g.L
+    g.set_j_particles(idh, mh, xh, vh)                      # every rank holds all particles
+    S.attach_peers(L, nh)
+    per = ((nh + world - 1) // world + 255) // 256 * 256      # windows on tile boundaries
+    lo, hi = min(nh, rank * per), min(nh, (rank + 1) * per)
+    assert L.g6x_hermite_set_shard(lo, max(hi, lo)) == 0
+    L.g6x_hermite_init(nh, 0.0, eta, eps2, None)
+    st = np.zeros(4)
+    torch.cuda.synchronize(); dist.barrier()
+    L.g6x_hermite_evolve(nh, t_end, eta, eps2, 0, st)
+    sharded = state(g)
+    if L.g6x_peer_error():
+        ok = False; msgs.append("peer error flag set (hermite)")
+    # all ranks must hold the same replica, bit for bit
+    xs = torch.from_numpy(sharded[1]).to(dev); chk = xs.clone(); dist.all_reduce(chk, op=dist.ReduceOp.MAX)
+    same_replica = bool((chk == xs).all().item())
+    g.close()
+    dist.barrier()
+    if rank == 0:                                           # the same run on one device
+        g1 = g6lib.G6(local)
+        g1.set_j_particles(idh, mh, xh, vh)
+        g1.L.g6x_hermite_init(nh, 0.0, eta, eps2, None)
+        st1 = np.zeros(4)
+        g1.L.g6x_hermite_evolve(nh, t_end, eta, eps2, 0, st1)
+        single = state(g1)
+        g1.close()
+        dx = np.abs(sharded[1] - single[1]).max()
+        same_steps = (st[1] == st1[1]) and (st[2] == st1[2])
+        if not (dx < 1e-9 and same_steps and same_replica):
+            ok = False
+        msgs.append("sharded Hermite N=%d to t=%g: %d block steps %.3f s (%.0f us/step) vs one device %d steps %.3f s; "
+                    "max |dx| %.1e, replicas identical %s" % (nh, t_end, st[1], st[3], 1e6 * st[3] / max(1, st[1]), st1[1],
+                                                             st1[3], dx, same_replica))
+    dist.barrier()
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-    g.close()
     if rank == 0:
         print(("MULTI-GPU OK " if flag.item() else "MULTI-GPU FAILED ") + "world=%d n=%d | " % (world, n) + " | ".join(msgs))
     dist.destroy_process_group()
