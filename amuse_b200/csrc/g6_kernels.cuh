@@ -1,15 +1,26 @@
 // g6_kernels.cuh -- hand-written sm_100a kernels of the B200 g6 force library.
 //
-//   predict_kernel   j-particle Hermite predictor   (HBM-bound)
-//   scatter_kernel   j-update scatter               (HBM/latency-bound)
-//   pack_i_kernel    double -> double-single i-block packing (device callers)
-//   force_kernel<>   Hermite force: acc, jerk, pot, nearest neighbour,
-//                    neighbour-sphere lists         (FP32-issue-bound)
-//   resolve_nn_kernel  id lookup after a cross-rank min-reduction
+//   predict_kernel          j-particle Hermite predictor                  (HBM-bound)
+//   scatter_kernel          j-update scatter                              (HBM/latency-bound)
+//   update_predict_kernel   scatter of a small update batch + predictor in one launch
+//   pack_i_kernel           double -> double-single i-block packing (device callers)
+//   force_fast_kernel<>     Hermite force, big i-blocks: acc, jerk, pot, nearest neighbour; mask-free groups of
+//                           pairs verified afterwards (speculative)       (FP32-pipe-bound)
+//   force_kernel<>          Hermite force, small i-blocks and neighbour-sphere lists: j split over the warps of a
+//                           CTA, masks per pair; optional i-block in the kernel parameters, results and completion
+//                           flag in mapped host memory, corrector in the output stage   (latency-bound)
+//   reduce_partials_kernel  sum of j-split partials, one warp per i
+//   resolve_nn_kernel       id lookup after a cross-rank min-reduction (NCCL path)
+//   peer_flag_kernel, peer_combine_kernel   multi-GPU exchange over peer memory (the force kernels store their
+//                           partials into the peers' buffers themselves, see store_outputs)
+//   hermite_*_kernel        device-resident Hermite block step: i-predictor, corrector + Aarseth step, write-back
+//   fp32_peak_kernel<>, latency_probe_kernel   roofline / latency-floor probes
 //
 // Reference behaviour being reproduced (not translated):
 //   force loop   src/amuse_ph4/src/idata.cc:198-236 (oracle, FP64)
-//   predictor    src/amuse_ph4/src/jdata.cc:726-747 (oracle, FP64)
+//   predictor    src/amuse_ph4/src/jdata.cc:726-747, i-predictor idata.cc:347-365 (oracle, FP64)
+//   corrector    src/amuse_ph4/src/idata.cc:443-511, first step jdata.cc:503-548 (oracle, FP64)
+//   reduction    src/amuse_ph4/src/idata.cc:284-313 (sum / min / owner's nn over the j-domains)
 //   API/semantics lib/sapporo_light/dev_evaluate_gravity.cu:46-106 (DS positions,
 //                self-exclusion by id :76-79, neighbour rule :60-72)
 #pragma once
