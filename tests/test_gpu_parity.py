@@ -280,6 +280,33 @@ def test_big_update_batches_flush_early_and_last_write_still_wins(g6):
     check_nn(out["nn"], ref["nn"], ids, x[:300], x)
 
 
+def test_empty_calls_and_extreme_ids(g6):
+    """Degenerate calls the callers can make: a force call before any j-particle exists (BHTree opens the
+    device long before its first list), an empty i-block, ids far beyond 2^24 (sapporo_light returns the
+    neighbour id through a float, sapporo.cpp:226-227; ph4's binaries get ids of 1e7 and more,
+    test_multiples2.py:254) and negative ids, a softening far larger than the system."""
+    O = _O()
+    g6.close()
+    assert g6.L.g6_open_(C.byref(g6.cid)) == 0                 # fresh device state: no j-memory at all
+    g6.nj = 0
+    g6.set_ti(0.0)
+    x3 = np.array([[0.1, 0.2, 0.3], [1.0, -1.0, 0.5], [0.0, 0.0, 0.0]]); v3 = np.zeros((3, 3))
+    out = g6.calc(np.array([5, 6, 7], dtype=np.int32), x3, v3, 1e-4, nj=0)
+    assert np.all(out["acc"] == 0) and np.all(out["jerk"] == 0) and np.all(out["pot"] == 0) and np.all(out["nn"] == -1)
+    n = 1500
+    m, x, v = P.new_plummer_model(n, seed=17)
+    ids = ((1 << 30) + 7 * np.arange(n)).astype(np.int32)
+    ids[::3] = -2 - np.arange(len(ids[::3]), dtype=np.int32)    # a third of them negative (not -1: field points)
+    _fresh(g6, ids, m, x, v)
+    out = g6.calc(ids[:0], x[:0], v[:0], 1e-4)                  # empty i-block: nothing to do, nothing to wait for
+    assert out["acc"].shape == (0, 3)
+    for eps2 in (0.0, 1e4):
+        out = g6.calc(ids[:200], x[:200], v[:200], eps2)
+        ref = O.force(x[:200], v[:200], m, x, v, eps2, iid=ids[:200], jid=ids, scales=True)
+        check_forces(out, ref, what="extreme ids eps2=%g" % eps2)
+        assert np.array_equal(out["nn"], ids[ref["nn"]])
+
+
 def test_neighbour_lists(g6):
     O = _O()
     m, x, v = P.new_plummer_model(3000, seed=8)
