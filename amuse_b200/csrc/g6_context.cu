@@ -35,6 +35,14 @@ using namespace g6b;
         }                                                                                          \
     } while (0)
 
+// G6_B200_TRACE: add the time since the last mark to phase k (needs locals t0, t1)
+#define G6_TR(k)                      \
+    if (G.trace) {                    \
+        t1 = wall();                  \
+        G.tr[k] += t1 - t0;           \
+        t0 = t1;                      \
+    }
+
 namespace {
 
 // Force-kernel variants (g6x_set_variant ids).
@@ -282,6 +290,26 @@ void require_open(const char *fn)
 }
 
 void run_predictor(int nj);
+
+// Spin on the completion flag a kernel raises in mapped host memory (latency path, Hermite step).  Every
+// ~1M polls the stream is queried, so that a failed kernel ends the wait with its CUDA error.
+void wait_flag(unsigned long long want, const char *what)
+{
+    volatile unsigned long long *flag = G.h_flag;
+    unsigned long long spins = 0;
+    while (*flag != want) {
+        if ((++spins & 0xfffff) == 0) {
+            cudaError_t q = cudaStreamQuery(G.stream);
+            if (q == cudaSuccess) {
+                if (*flag == want) break;
+                fprintf(stderr, "g6_b200: FATAL %s finished without raising its completion flag\n", what);
+                exit(-1);
+            }
+            if (q != cudaErrorNotReady) CK(q);
+        }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+}
 
 // The pending batch has been handed to a kernel on the stream: forget it on the host side and switch
 // to the other pinned buffer (its consumer of two flushes ago is long complete; the event wait is a
@@ -876,12 +904,6 @@ void g6calc_firsthalf_(int *cluster_id, int *nj, int *ni, int index[], double xi
     }
     if (G.pending) CK(cudaStreamSynchronize(G.stream));  // a firsthalf without its lasthalf
     double t0 = G.trace ? wall() : 0.0, t1 = 0.0;
-#define G6_TR(k)                      \
-    if (G.trace) {                    \
-        t1 = wall();                  \
-        G.tr[k] += t1 - t0;           \
-        t0 = t1;                      \
-    }
     // scatter (small batches: fused with the predictor, records read from mapped pinned memory) + predict
     const bool inl = (n > 0) && (n <= G.inline_max) && (G.variant == V_AUTO);
     predict_with_updates(*nj);
@@ -945,22 +967,7 @@ static int lasthalf_common(int nj, int ni, double acc[][3], double jerk[][3], do
     if (ni > 0) {
         double t0 = G.trace ? wall() : 0.0, t1 = 0.0;
         if (G.cur_direct) {
-            // spin on the flag the kernel raises in mapped host memory
-            volatile unsigned long long *flag = G.h_flag;
-            const unsigned long long want = G.flag_seq;
-            unsigned long long spins = 0;
-            while (*flag != want) {
-                if ((++spins & 0xfffff) == 0) {   // every ~1M polls: is the stream still healthy?
-                    cudaError_t q = cudaStreamQuery(G.stream);
-                    if (q == cudaSuccess) {
-                        if (*flag == want) break;
-                        fprintf(stderr, "g6_b200: FATAL force kernel finished without raising its completion flag\n");
-                        exit(-1);
-                    }
-                    if (q != cudaErrorNotReady) CK(q);
-                }
-            }
-            std::atomic_thread_fence(std::memory_order_acquire);
+            wait_flag(G.flag_seq, "force kernel");
             G6_TR(6)
         } else {
             const size_t bytes = sizeof(double) * 7 * (size_t)ni + (nn ? sizeof(int) * (size_t)ni : 0);
@@ -1479,20 +1486,7 @@ static void hermite_pass(int nj, int n, double tnext, double eta, double eps2, i
         G.launches += 2;
     }
     G.j_dirty = true;   // the active particles' state changed: predict again before the next force
-    volatile unsigned long long *flag = G.h_flag;
-    unsigned long long spins = 0;
-    while (*flag != h.flag_seq) {
-        if ((++spins & 0xfffff) == 0) {
-            cudaError_t q = cudaStreamQuery(G.stream);
-            if (q == cudaSuccess) {
-                if (*flag == h.flag_seq) break;
-                fprintf(stderr, "g6_b200: FATAL Hermite step finished without raising its completion flag\n");
-                exit(-1);
-            }
-            if (q != cudaErrorNotReady) CK(q);
-        }
-    }
-    std::atomic_thread_fence(std::memory_order_acquire);
+    wait_flag(h.flag_seq, "Hermite step");
 }
 
 int g6x_hermite_step(int nj, int ni, const int *ilist, double tnext, double eta, double eps2, const double *old_dt,
