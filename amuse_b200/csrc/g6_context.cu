@@ -1440,7 +1440,8 @@ static void hermite_pass(int nj, int n, double tnext, double eta, double eps2, i
         // replicated state, sharded forces: gather the block (every rank, identical), predict only this
         // rank's j-window, sum over it with the partials mirrored into the peers' exchange buffers, combine,
         // and let every rank correct its own replica with the identical totals
-        const int lo = H.shard_lo, hi = std::min(H.shard_hi, std::min(nj, G.capacity));
+        int lo = H.shard_lo, hi = std::min(H.shard_hi, std::min(nj, G.capacity));
+        if (hi <= lo) lo = hi = 0;   // empty window (more ranks than j-tiles): this rank contributes zeros
         hermite_gather_kernel<<<ctas, 256, 0, G.stream>>>(h);
         CK(cudaGetLastError());
         if (hi > lo) {

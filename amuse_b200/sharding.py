@@ -37,6 +37,17 @@ def define_domain(nj, size, rank):
     return j_start, min(j_end, nj)
 
 
+def define_window(nj, size, rank, tile=256):
+    """[j_lo, j_hi) of `rank` for the sharded device-resident Hermite step (``g6x_hermite_set_shard``): like
+    define_domain, but the windows start on j-tile boundaries (the force kernel's per-tile id ranges and
+    FP32 summation groups then coincide with the single-device run, which makes the trajectories
+    bit-identical).  Ranks beyond the last tile get an empty window."""
+    per = ((nj + size - 1) // size + tile - 1) // tile * tile
+    lo = rank * per                       # always a tile boundary, possibly beyond nj (empty window)
+    hi = min(nj, (rank + 1) * per)
+    return lo, max(lo, hi)
+
+
 def combine_partials(d_sum, d_key, resolve_ids, group=None):
     """In-place cross-rank combination.
 

@@ -107,9 +107,8 @@ def main():
     L = g.L
     g.set_j_particles(idh, mh, xh, vh)                      # every rank holds all particles
     S.attach_peers(L, nh)
-    per = ((nh + world - 1) // world + 255) // 256 * 256      # windows on tile boundaries
-    lo, hi = min(nh, rank * per), min(nh, (rank + 1) * per)
-    assert L.g6x_hermite_set_shard(lo, max(hi, lo)) == 0
+    lo, hi = S.define_window(nh, world, rank)                 # windows on tile boundaries
+    assert L.g6x_hermite_set_shard(lo, hi) == 0
     L.g6x_hermite_init(nh, 0.0, eta, eps2, None)
     st = np.zeros(4)
     torch.cuda.synchronize(); dist.barrier()

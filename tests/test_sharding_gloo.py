@@ -87,3 +87,17 @@ def test_define_domain_matches_oracle_restatement():
             for rank in range(size):
                 a, b = O.define_domain(nj, size, rank)
                 assert S.define_domain(nj, size, rank) == (a, min(b, nj))
+
+
+def test_define_window_tiles_the_address_range_on_tile_boundaries():
+    from amuse_b200 import sharding as S
+    for nj in (1, 255, 256, 257, 4096, 20000, 1153434):
+        for size in (1, 2, 3, 8):
+            w = [S.define_window(nj, size, r) for r in range(size)]
+            covered = 0
+            for lo, hi in w:
+                assert lo % 256 == 0 and lo <= hi
+                if hi > lo:                      # non-empty windows follow each other without gaps
+                    assert lo == covered and hi <= nj
+                    covered = hi
+            assert covered == nj

@@ -30,9 +30,8 @@ g = g6lib.G6(local)
 g.set_j_particles(ids, m, x, v)
 if world > 1:
     S.attach_peers(g.L, nt)
-    per = ((nt + world - 1) // world + 255) // 256 * 256
-    lo, hi = min(nt, rank * per), min(nt, (rank + 1) * per)
-    g.L.g6x_hermite_set_shard(lo, max(lo, hi))
+    lo, hi = S.define_window(nt, world, rank)
+    g.L.g6x_hermite_set_shard(lo, hi)
 import time
 t0 = time.perf_counter()
 g.L.g6x_hermite_init(nt, 0.0, 0.14, eps2, None)
