@@ -297,8 +297,14 @@ void wait_flag(unsigned long long want, const char *what)
 {
     volatile unsigned long long *flag = G.h_flag;
     unsigned long long spins = 0;
+    double t_start = 0.0;
     while (*flag != want) {
         if ((++spins & 0xfffff) == 0) {
+            if (t_start == 0.0) t_start = wall();
+            if (wall() - t_start > 300.0) {   // nothing on this path runs for minutes: do not hang the caller forever
+                fprintf(stderr, "g6_b200: FATAL %s did not complete within 300 s\n", what);
+                exit(-1);
+            }
             cudaError_t q = cudaStreamQuery(G.stream);
             if (q == cudaSuccess) {
                 if (*flag == want) break;
