@@ -1128,6 +1128,26 @@ void force_j_particle_send(void)
 {
     if (G.open) flush_updates();
 }
+int get_j_part_data(int addr, int nj, double *pos, double *vel, double *acc, double *jrk, double *ppos, double *pvel)
+{
+    require_open("get_j_part_data");
+    flush_updates();
+    if (addr < 0 || addr >= nj || addr >= G.capacity) return -1;
+    double2 q[7];
+    float4 abc[3];
+    CK(cudaStreamSynchronize(G.stream));
+    for (int k = 0; k < 7; k++) CK(cudaMemcpy(&q[k], G.js.q[k] + addr, sizeof(double2), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&abc[0], G.js.A + addr, sizeof(float4), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&abc[1], G.js.B + addr, sizeof(float4), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&abc[2], G.js.C + addr, sizeof(float4), cudaMemcpyDeviceToHost));
+    if (pos) { pos[0] = q[0].x; pos[1] = q[0].y; pos[2] = q[1].x; }
+    if (vel) { vel[0] = q[2].x; vel[1] = q[2].y; vel[2] = q[3].x; }
+    if (acc) { acc[0] = q[3].y; acc[1] = q[4].x; acc[2] = q[4].y; }
+    if (jrk) { jrk[0] = q[5].x; jrk[1] = q[5].y; jrk[2] = q[6].x; }
+    if (ppos) { ppos[0] = (double)abc[0].x + abc[1].x; ppos[1] = (double)abc[0].y + abc[1].y; ppos[2] = (double)abc[0].z + abc[1].z; }
+    if (pvel) { pvel[0] = abc[2].x; pvel[1] = abc[2].y; pvel[2] = abc[2].z; }
+    return 0;
+}
 
 // ===========================================================================
 // Part 2: g6x_ extensions

@@ -25,7 +25,7 @@ G6_SYMBOLS = [
     "g6calc_firsthalf", "g6calc_lasthalf", "g6calc_lasthalf2", "g6_initialize_jp_buffer",
     "g6_flush_jp_buffer", "g6_reset", "g6_reset_fofpga", "g6_reinitialize", "g6_get_number_of_pipelines",
     "g6_read_neighbour_list", "g6_get_neighbour_list", "g6_set_neighbour_list_sort_mode",
-    "g6_get_neighbour_list_sort_mode", "g6_set_overflow_flag_test_mode", "force_j_particle_send",
+    "g6_get_neighbour_list_sort_mode", "g6_set_overflow_flag_test_mode", "force_j_particle_send", "get_j_part_data",
     "g6x_version", "g6x_set_stream", "g6x_set_refine", "g6x_set_j_offset", "g6x_set_j_particles", "g6x_predict",
     "g6x_calc_device", "g6x_device_chunk", "g6x_resolve_nn", "g6x_synchronize", "g6x_launch_count", "g6x_get_predicted",
     "g6x_read_predicted", "g6x_time_predictor", "g6x_set_variant", "g6x_fp32_peak",
@@ -78,6 +78,7 @@ def load():
     L.g6x_hermite_evolve.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, C.c_longlong, _dp]
     L.g6x_hermite_evolve.restype = C.c_longlong
     L.g6x_hermite_get_state.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.get_j_part_data.argtypes = [C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp]
     L.g6x_hermite_set_shard.argtypes = [C.c_int, C.c_int]
     L.g6x_latency_probe.argtypes = [C.c_int, C.c_int]
     L.g6x_latency_probe.restype = C.c_double

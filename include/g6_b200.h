@@ -123,9 +123,14 @@ int g6_get_neighbour_list(int clusterid, int ipipe, int maxlength, int *nblen,
                           int nbl[]);
 void g6_set_neighbour_list_sort_mode(int mode);
 int g6_get_neighbour_list_sort_mode(void);
-/* Debug hooks ph4 declares (grape.h:110-119); harmless stubs. */
+/* Debug hooks ph4 declares (grape.h:110-119). */
 int g6_set_overflow_flag_test_mode(int aflag, int jflag, int pflag);
 void force_j_particle_send(void);
+/* grape.h:118-119 (its only call site is commented out, gpu.cc:423): read back j-particle `addr` of a
+ * j-memory of nj particles -- stored pos, vel, acc, jerk and the last predicted pos, vel.  Returns 0, or
+ * -1 if addr is outside [0, nj). */
+int get_j_part_data(int addr, int nj, double *pos, double *vel, double *acc,
+                    double *jrk, double *ppos, double *pvel);
 
 /* ======================================================================
  * Part 2 -- g6x_: batched and device-resident entry points

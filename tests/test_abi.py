@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _header_symbols():
     src = open(os.path.join(ROOT, "include", "g6_b200.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(g6x?_?\w*|g6calc_\w+|get_device_count|force_j_particle_send)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(g6x?_?\w*|g6calc_\w+|get_device_count|get_j_part_data|force_j_particle_send)\s*\(", src)))
 
 
 @pytest.fixture(scope="module")

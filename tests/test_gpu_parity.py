@@ -307,6 +307,26 @@ def test_empty_calls_and_extreme_ids(g6):
         assert np.array_equal(out["nn"], ids[ref["nn"]])
 
 
+def test_debug_readback_of_a_j_particle(g6):
+    """get_j_part_data (grape.h:118-119): stored state and last prediction of one j-particle."""
+    O = _O()
+    n = 300
+    m, x, v = P.new_plummer_model(n, seed=19)
+    ids = np.arange(1, n + 1, dtype=np.int32)
+    rnd = np.random.RandomState(2)
+    acc = rnd.standard_normal((n, 3)); jerk = rnd.standard_normal((n, 3)); tj = -2.0 ** -rnd.randint(3, 8, n)
+    _fresh(g6, ids, m, x, v, acc=acc, jerk=jerk, tj=tj, ti=0.0)
+    g6.predict(0.0)
+    pp, pv = O.predict(0.0, tj, x, v, acc, jerk)
+    out = [np.zeros(3) for _ in range(6)]
+    for j in (0, 17, n - 1):
+        assert g6.L.get_j_part_data(j, n, *out) == 0
+        assert np.array_equal(out[0], x[j]) and np.array_equal(out[1], v[j])
+        assert np.allclose(out[2], acc[j], rtol=1e-15) and np.allclose(out[3], jerk[j], rtol=1e-15)
+        assert np.allclose(out[4], pp[j], rtol=2e-14, atol=1e-15) and np.allclose(out[5], pv[j], rtol=2e-7, atol=1e-9)
+    assert g6.L.get_j_part_data(n, n, *out) == -1
+
+
 def test_neighbour_lists(g6):
     O = _O()
     m, x, v = P.new_plummer_model(3000, seed=8)
