@@ -934,10 +934,10 @@ __global__ void __launch_bounds__(THREADS, MINB) force_kernel(const ForceArgs p,
 // found at the end by re-scanning that one group with the same r2 instruction sequence.
 // ---------------------------------------------------------------------------
 #ifndef G6_GRP
-#define G6_GRP 16
+#define G6_GRP 32
 #endif
 #ifndef G6_FUNROLL
-#define G6_FUNROLL 1
+#define G6_FUNROLL 2
 #endif
 #ifndef G6_DUAL
 #define G6_DUAL 0   // 0: one FP32 partial-sum set per group; k: two sets (even/odd j) in kernels with IPT >= k

@@ -180,9 +180,11 @@ def test_speculative_kernel_equals_masked_kernel(g6, variant):
             check_forces(out, ref, what="speculative v%d eps2=%g" % (variant, eps2))
             check_nn(out["nn"], ref["nn"], ids, xi, xj)
             assert np.array_equal(out["nn"], masked["nn"])
-            # same arithmetic per pair, different summation grouping only
-            assert rel_vec_err(out["acc"], masked["acc"]).max() < 5e-7
-            assert rel_err(out["pot"], masked["pot"]).max() < 5e-7
+            # same arithmetic per pair, different summation grouping only (FP32 partial sums over 32 pairs here,
+            # 16 in the masked kernel): both are within 1e-6 of the oracle (checked above for `out`), and a wrong
+            # mask or a lost group would show as an O(1) difference
+            assert rel_vec_err(out["acc"], masked["acc"]).max() < 1e-6
+            assert rel_err(out["pot"], masked["pot"]).max() < 1e-6
             assert np.array_equal(out_nonn["acc"], out["acc"]) and np.array_equal(out_nonn["pot"], out["pot"])
 
 
