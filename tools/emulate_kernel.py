@@ -25,7 +25,7 @@ def split(x):
     return h, (x - h.astype(F)).astype(f)
 
 
-def emulate(ipos, ivel, iid, m, x, v, jid, eps2, newton="B", grp=16, dual=False, mufu_err=2 ** -22.9, seed=0,
+def emulate(ipos, ivel, iid, m, x, v, jid, eps2, newton="B", grp=32, dual=False, mufu_err=2 ** -22.9, seed=0,
             exact=()):
     """exact: subset of {'geom','rsqrt','mr3','acc_sum'} evaluated in FP64 instead (attribution)."""
     rnd = np.random.RandomState(seed)
@@ -149,11 +149,11 @@ if __name__ == "__main__":
     kappa = ref["sacc"] / np.linalg.norm(ref["acc"], axis=1)
     print("case %s: ni %d nj %d; cancellation sum|a_ij|/|a_i|: median %.1f max %.1f" % (
         name, len(args[0]), len(args[3]), np.median(kappa), kappa.max()))
-    for label, kw in [("newton A grp16", dict(newton="A")), ("newton B grp16", dict(newton="B")),
-                      ("newton B grp8", dict(newton="B", grp=8)), ("newton B grp32", dict(newton="B", grp=32)),
+    for label, kw in [("newton A grp32", dict(newton="A")), ("newton B grp32 (the kernel)", dict(newton="B")),
+                      ("newton B grp8", dict(newton="B", grp=8)), ("newton B grp16", dict(newton="B", grp=16)),
                       ("newton B grp32 dual", dict(newton="B", grp=32, dual=True)),
                       ("newton B grp64 dual", dict(newton="B", grp=64, dual=True)),
-                      ("raw mufu grp16", dict(newton="none")),
+                      ("raw mufu grp32", dict(newton="none")),
                       ("B, exact geom", dict(exact=("geom",))), ("B, exact rsqrt", dict(exact=("rsqrt",))),
                       ("B, exact mr3..", dict(exact=("mr3",))), ("B, exact sums", dict(exact=("acc_sum",))),
                       ("B, exact rsqrt+sums", dict(exact=("rsqrt", "acc_sum")))]:
