@@ -196,6 +196,24 @@ def correct(tnext, eta, itime, itimestep, old_acc, old_jerk, iacc, ijerk, ipos, 
     return p, v, t, dt
 
 
+def check_encounters(iid, inn, idnn, imass, iradius, jid, jmass, jradius, rmin, jvel=None, use_ref=False):
+    """idata::check_encounters restatement (or the reference with use_ref): returns (close1, close2, coll1, coll2)."""
+    out = np.zeros(4, dtype=np.int32)
+    ni, nj = len(iid), len(jid)
+    if use_ref:
+        L = ref()
+        L.ph4ref_check_encounters.argtypes = [C.c_int, _ip, _dp, _dp, _dp, C.c_int, _ip, _ip, _dp, _dp, _dp, C.c_double, _ip]
+        jv = _c(jvel) if jvel is not None else np.zeros((nj, 3))
+        L.ph4ref_check_encounters(nj, _c(jid, np.int32), _c(jmass), _c(jradius), jv, ni, _c(iid, np.int32),
+                                  _c(inn, np.int32), _c(idnn), _c(imass), _c(iradius), float(rmin), out)
+    else:
+        L = lib()
+        L.oracle_check_encounters.argtypes = [C.c_int, _ip, _ip, _dp, _dp, _dp, _ip, _dp, _dp, C.c_double, _ip]
+        L.oracle_check_encounters(ni, _c(iid, np.int32), _c(inn, np.int32), _c(idnn), _c(imass), _c(iradius),
+                                  _c(jid, np.int32), _c(jmass), _c(jradius), float(rmin), out)
+    return tuple(int(v) for v in out)
+
+
 def initial_timestep(system_time, eta, acc, jerk):
     """jdata::set_initial_timestep restatement (jdata.cc:503-548)."""
     n = len(acc)

@@ -314,3 +314,45 @@ void oracle_initial_timestep(int nj, double system_time, double eta, const doubl
         timestep[j] = firststep;
     }
 }
+
+/*
+ * Close-encounter / collision detection over the current i-list, follows idata::check_encounters(),
+ * src/amuse_ph4/src/idata.cc:634-733 (the nearest-neighbour branch): the i-particle with the largest
+ * rmin/dnn (>= 1) defines the close pair, the one with the largest (r_i + r_nn)/dnn (>= 1) the colliding
+ * pair; pairs of two massless particles are ignored; first maximum wins (strict >).
+ * inn = j index of the nearest neighbour (-1: none), idnn its distance.  out[4] = close1, close2, coll1, coll2
+ * (ids; -1 if none).
+ */
+void oracle_check_encounters(int ni, const int *iid, const int *inn, const double *idnn, const double *imass,
+                             const double *iradius, const int *jid, const double *jmass, const double *jradius,
+                             double rmin, int *out)
+{
+    double rmax_close = 0, rmax_coll = 0;
+    int imax_close = -1, imax_coll = -1;
+    out[0] = out[1] = out[2] = out[3] = -1;
+    for (int i = 0; i < ni; i++) {
+        int jnn = inn[i];
+        if (jnn >= 0) {
+            if ((jmass[jnn] > ORACLE_TINY) || (imass[i] > ORACLE_TINY)) {
+                double r = rmin / idnn[i];
+                if (r > rmax_close) {
+                    rmax_close = r;
+                    imax_close = i;
+                }
+                r = (iradius[i] + jradius[jnn]) / idnn[i];
+                if (r > rmax_coll) {
+                    rmax_coll = r;
+                    imax_coll = i;
+                }
+            }
+        }
+    }
+    if (rmax_close >= 1) {
+        out[0] = iid[imax_close];
+        out[1] = jid[inn[imax_close]];
+    }
+    if (rmax_coll >= 1) {
+        out[2] = iid[imax_coll];
+        out[3] = jid[inn[imax_coll]];
+    }
+}

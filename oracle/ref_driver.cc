@@ -191,6 +191,37 @@ int ph4ref_correct(int ni, double tnext, double eta, double *itime, double *itim
     return 0;
 }
 
+// idata::check_encounters() (src/amuse_ph4/src/idata.cc:618-733) on caller-supplied nearest-neighbour data.
+// jmass/jradius/jid describe the j system (nj particles), the i-arrays the current block.
+// out[4] = close1, close2, coll1, coll2.
+int ph4ref_check_encounters(int nj, const int *jid, const double *jmass, const double *jradius, const double *jvel,
+                            int ni, const int *iid, const int *inn, const double *idnn, const double *imass,
+                            const double *iradius, double rmin, int *out)
+{
+    quiet q;
+    jdata jd;
+    for (int j = 0; j < nj; j++) {
+        vec p(0.0, 0.0, 0.0), v(jvel[3 * j], jvel[3 * j + 1], jvel[3 * j + 2]);
+        jd.add_particle(jmass[j], jradius[j], p, v, jid[j]);
+    }
+    jd.rmin = rmin;
+    jd.use_gpu = false;
+    idata id_;
+    id_.jdat = &jd;
+    id_.set_ni(ni);
+    id_.ni = ni;
+    for (int i = 0; i < ni; i++) {
+        id_.iid[i] = iid[i];
+        id_.inn[i] = inn[i];
+        id_.idnn[i] = idnn[i];
+        id_.imass[i] = imass[i];
+        id_.iradius[i] = iradius[i];
+    }
+    id_.check_encounters();
+    out[0] = jd.close1; out[1] = jd.close2; out[2] = jd.coll1; out[3] = jd.coll2;
+    return 0;
+}
+
 // Run the reference Hermite integrator to t_end (the loop of
 // src/amuse_ph4/interface.cc:673-674 / parallel_hermite_4.cc run_hermite4).
 // use_gpu selects the g6 ABI path when compiled -DGPU.
