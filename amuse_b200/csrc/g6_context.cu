@@ -14,6 +14,8 @@
 #include "g6_kernels.cuh"
 #include "../../include/g6_b200.h"
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include <algorithm>
 #include <atomic>
 #include <chrono>
@@ -84,13 +86,36 @@ struct Context {
     int capacity = 0;  // slots allocated (multiple of TILE)
     int nj_hi = 0;     // 1 + highest address ever set
     JState js{};
+    // j-memory order (rebuild_order): Morton permutation address -> slot, id table, neighbour bounds
+    int *addr_of = nullptr;            // [slot] -> address (device)
+    JState js2{};                      // second set of state arrays the permutation gathers into
+    int *addr_of2 = nullptr;
+    std::vector<int> h_slot_of;        // host mirror of js.slot_of
+    std::vector<int> h_id;             // id last staged for every address (detects id changes)
+    unsigned *d_keys = nullptr, *d_keys_tmp = nullptr;   // [capacity] sorted Morton keys / sort input
+    int *d_vals = nullptr, *d_vals_tmp = nullptr;
+    void *d_sort_tmp = nullptr;
+    size_t sort_tmp_bytes = 0;
+    int sort_cap = 0;
+    int *d_box = nullptr, *h_box = nullptr;   // 6 ordered ints
+    u64 *d_hash = nullptr;
+    unsigned hash_size = 0;
+    OrderInfo ord{};
+    bool order_valid = false;
+    int order_nj = -1;
+    bool ids_dirty = false;
+    long long updates_since_order = 0, updates_since_force = 0;
+    long long order_rebuilds = 0;
+    float kclose = 16.f;               // G6_B200_KCLOSE
+    float farc = 0.125f;               // G6_B200_FARC
+    int near_w = 32;                   // Morton window (each side) of the neighbour-bound scans
     double ti = 0.0;
     double predicted_ti = 0.0;
     int predicted_nj = -1;  // prefix predicted at predicted_ti (-1: none)
     bool j_dirty = false;
 
     // staging of j-updates
-    std::vector<int> slot_of_addr;  // address -> slot in the pending batch, -1
+    std::vector<int> pending_of_addr;  // address -> position in the pending batch, -1
     JUpdate *h_up = nullptr;        // pinned batch being filled (= h_up2[up_cur])
     JUpdate *h_up2[2] = {nullptr, nullptr};   // two pinned batches: one fills while the other uploads
     cudaEvent_t up_done[2] = {nullptr, nullptr};
@@ -99,14 +124,22 @@ struct Context {
     int up_cap = 0, up_n = 0;
 
     // i-block buffers (npipes)
-    float4 *h_i = nullptr;  // pinned [3][npipes]
-    float4 *d_i = nullptr;  // [3][npipes]
+    float4 *h_i = nullptr;  // pinned [4][npipes]
+    float4 *d_i = nullptr;  // [4][npipes]
+    int *d_conf = nullptr;  // [npipes] slot of the j-particle with the i-particle's id
+    std::vector<int> h_perm;   // packed position k of the pending i-block holds caller particle h_perm[k] (empty: identity)
+    std::vector<unsigned> h_ikey, h_ikey2;
+    std::vector<int> h_perm2;
     double *d_sum = nullptr;  // [7n doubles][n nearest-neighbour ids] of the current i-block
     u64 *d_key = nullptr;
     double *h_sum = nullptr;  // pinned, same layout
     // device-resident entry point scratch
-    float4 *d_i2 = nullptr;
+    float4 *d_i2 = nullptr;   // [4][i2_cap]
+    int *d_conf2 = nullptr;   // [i2_cap]
     int i2_cap = 0;
+    unsigned *d_ikey = nullptr, *d_ikey_tmp = nullptr;   // Morton sort of a device-resident i-set
+    int *d_iperm = nullptr, *d_iperm_tmp = nullptr;
+    int isort_cap = 0;
     // partial workspace
     double *part_sum = nullptr;
     u64 *part_key = nullptr;
@@ -143,7 +176,7 @@ struct Context {
 
     // multi-GPU exchange over peer memory (g6x_peer_*): see g6_kernels.cuh "Multi-GPU exchange"
     struct Peer {
-        bool allocated = false, attached = false;
+        bool allocated = false, attached = false, ipc = true;
         int world = 1, rank = 0, cap = 0;
         unsigned char *buf = nullptr;            // own exchange buffer: [2 halves][world slots] + flags[2][world]
         unsigned char *peer_buf[MAX_PEERS + 1] = {};   // all ranks' buffers as seen from here ([rank] = buf)
@@ -169,7 +202,8 @@ struct Context {
         double *d_pred = nullptr;                              // [cap][6]
         int *d_ilist = nullptr;                                // device copies of the block's addresses / steps
         double *d_olddt = nullptr;
-        float4 *d_i = nullptr;                                 // [3][cap]
+        float4 *d_i = nullptr;                                 // [4][cap]
+        int *d_conf = nullptr;                                 // [cap]
         double *d_sum = nullptr;                               // [cap][7]
         u64 *d_key = nullptr;
         int *d_nnid = nullptr;
@@ -191,7 +225,12 @@ struct Context {
     bool pending = false;
 };
 
-Context G;
+// One context per CUDA device the process has opened; the g6 calls work on the current one.  With
+// G6_B200_DEVICES > 1 the ABI layer ("multi-device" below) drives several of them as one j-memory.
+constexpr int MAX_DEVICES = MAX_PEERS + 1;
+Context g_ctx[MAX_DEVICES];
+Context *g_cur = &g_ctx[0];
+#define G (*g_cur)
 
 int env_int(const char *name, int dflt)
 {
@@ -214,7 +253,7 @@ void dev_free(T *&p)
 template <typename T>
 void host_alloc(T *&p, size_t n)
 {
-    CK(cudaHostAlloc((void **)&p, std::max<size_t>(n, 1) * sizeof(T), cudaHostAllocMapped));
+    CK(cudaHostAlloc((void **)&p, std::max<size_t>(n, 1) * sizeof(T), cudaHostAllocMapped | cudaHostAllocPortable));
 }
 template <typename T>
 T *dev_alias(T *host_ptr)
@@ -253,12 +292,35 @@ void ensure_capacity(int need)
     newcap = (newcap + TILE - 1) / TILE * TILE;
     size_t old = G.capacity;
     for (int k = 0; k < 7; k++) grow_dev(G.js.q[k], old, newcap, G.stream);
+    grow_dev(G.js.ia, old, newcap, G.stream);
     grow_dev(G.js.A, old, newcap, G.stream);
     grow_dev(G.js.B, old, newcap, G.stream);
     grow_dev(G.js.C, old, newcap, G.stream);
+    grow_dev(G.js.L, old, newcap, G.stream);
+    grow_dev(G.js.gbb, old / TILE * TBOX, newcap / TILE * TBOX, G.stream);
+    grow_dev(G.js.near2, old, newcap, G.stream);
+    grow_dev(G.js.slot_of, old, newcap, G.stream);
+    grow_dev(G.addr_of, old, newcap, G.stream);
+    order_fill_kernel<<<(unsigned)((newcap - old + 255) / 256), 256, 0, G.stream>>>((int)old, (int)newcap, G.js.slot_of,
+                                                                                  G.addr_of, G.js.near2);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(G.stream));
+    // the second set of arrays (target of the Morton permutation) and the sort buffers: no contents to keep
+    for (int k = 0; k < 7; k++) { dev_free(G.js2.q[k]); dev_alloc(G.js2.q[k], newcap); }
+    dev_free(G.js2.ia); dev_alloc(G.js2.ia, newcap);
+    dev_free(G.js2.near2); dev_alloc(G.js2.near2, newcap);
+    dev_free(G.addr_of2); dev_alloc(G.addr_of2, newcap);
+    dev_free(G.d_keys); dev_alloc(G.d_keys, newcap);
+    dev_free(G.d_keys_tmp); dev_alloc(G.d_keys_tmp, newcap);
+    dev_free(G.d_vals); dev_alloc(G.d_vals, newcap);
+    dev_free(G.d_vals_tmp); dev_alloc(G.d_vals_tmp, newcap);
     G.capacity = (int)newcap;
-    G.slot_of_addr.resize(newcap, -1);
+    G.pending_of_addr.resize(newcap, -1);
+    G.h_slot_of.resize(newcap);
+    for (size_t a = old; a < newcap; a++) G.h_slot_of[a] = (int)a;
+    G.h_id.resize(newcap, (int)0x80000000);
     G.predicted_nj = -1;
+    G.order_valid = false;   // the sorted keys lived in the old buffers
 }
 
 void ensure_up_cap(int need)
@@ -298,11 +360,14 @@ void wait_flag(unsigned long long want, const char *what)
     volatile unsigned long long *flag = G.h_flag;
     unsigned long long spins = 0;
     double t_start = 0.0;
+    // no wall-clock limit unless the caller sets one (G6_B200_WAIT_SECONDS): a full sweep of a very large
+    // system, or a shared GPU, may legitimately take minutes; real failures surface through cudaStreamQuery
+    static const int limit_s = env_int("G6_B200_WAIT_SECONDS", 0);
     while (*flag != want) {
         if ((++spins & 0xfffff) == 0) {
             if (t_start == 0.0) t_start = wall();
-            if (wall() - t_start > 300.0) {   // nothing on this path runs for minutes: do not hang the caller forever
-                fprintf(stderr, "g6_b200: FATAL %s did not complete within 300 s\n", what);
+            if (limit_s > 0 && wall() - t_start > (double)limit_s) {
+                fprintf(stderr, "g6_b200: FATAL %s did not complete within %d s (G6_B200_WAIT_SECONDS)\n", what, limit_s);
                 exit(-1);
             }
             cudaError_t q = cudaStreamQuery(G.stream);
@@ -323,7 +388,7 @@ void wait_flag(unsigned long long want, const char *what)
 void retire_batch()
 {
     CK(cudaEventRecord(G.up_done[G.up_cur], G.stream));
-    for (int k = 0; k < G.up_n; k++) G.slot_of_addr[G.h_up[k].addr] = -1;
+    for (int k = 0; k < G.up_n; k++) G.pending_of_addr[G.h_up[k].addr] = -1;
     G.up_n = 0;
     G.up_cur ^= 1;
     G.h_up = G.h_up2[G.up_cur];
@@ -355,7 +420,7 @@ void flush_updates()
 void fill_inline_updates(InlineU &iu)
 {
     iu.n = G.up_n;
-    for (int k = 0; k < G.up_n; k++) iu.addr[k] = G.h_up[k].addr;
+    for (int k = 0; k < G.up_n; k++) iu.slot[k] = G.h_up[k].slot;
 }
 
 // scatter (if any updates are pending) + predict, in as few launches as possible
@@ -391,6 +456,111 @@ void run_predictor(int nj)
     G.predicted_nj = n;
     G.predicted_ti = G.ti;
     G.j_dirty = false;
+}
+
+// ---- j-memory order ------------------------------------------------------------------------------
+// Sort the slots that hold addresses [0, nj) by the Morton key of their positions (addresses >= nj keep
+// slot == address order behind them), rebuild the id -> slot table and the neighbour bounds.  Called with
+// no update pending; everything runs on the library stream, two short host synchronisations (the box
+// comes back to fix the origin and the grid, the permutation to update the host mirror).
+void rebuild_order(int nj)
+{
+    nj = std::min(nj, G.capacity);
+    const int n = std::min(G.capacity, std::max(nj, G.nj_hi));
+    G.order_valid = true;
+    G.order_nj = nj;
+    G.ids_dirty = false;
+    G.updates_since_order = 0;
+    G.ord = OrderInfo{};
+    G.ord.kclose = G.kclose;
+    G.ord.farc2 = G.farc * G.farc;
+    if (n <= 0 || nj <= 0) return;
+    G.order_rebuilds++;
+    cudaStream_t st = G.stream;
+    const int blocks = (n + 255) / 256;
+    if (!G.d_box) {
+        dev_alloc(G.d_box, 8);
+        host_alloc(G.h_box, 8);
+    }
+    union { int i; float f; } cv;
+    auto ord_i = [&](float f) { cv.f = f; return cv.i >= 0 ? cv.i : cv.i ^ 0x7fffffff; };
+    auto ord_f = [&](int i) { cv.i = i >= 0 ? i : i ^ 0x7fffffff; return cv.f; };
+    for (int d = 0; d < 3; d++) {
+        G.h_box[d] = 0x7f7fffff;
+        G.h_box[3 + d] = ord_i(-3.0e38f);
+    }
+    CK(cudaMemcpyAsync(G.d_box, G.h_box, 6 * sizeof(int), cudaMemcpyHostToDevice, st));
+    order_box_kernel<<<blocks, 256, 0, st>>>(n, nj, G.js, G.addr_of, G.d_box);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(G.h_box, G.d_box, 6 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    double lo[3], hi[3], diag2 = 0.0;
+    for (int d = 0; d < 3; d++) {
+        lo[d] = ord_f(G.h_box[d]);
+        hi[d] = ord_f(G.h_box[3 + d]);
+        if (!(hi[d] >= lo[d])) lo[d] = hi[d] = 0.0;   // no massive particle
+        G.js.x0[d] = 0.5 * (lo[d] + hi[d]);
+        const double ext = hi[d] - lo[d];
+        diag2 += ext * ext;
+        G.ord.blo[d] = (float)(lo[d] - G.js.x0[d]);
+        G.ord.binv[d] = ext > 0.0 ? (float)(1023.999 / ext) : 0.f;
+    }
+    for (int d = 0; d < 3; d++) G.js2.x0[d] = G.js.x0[d];
+    G.ord.cap2 = (float)(diag2 / 64.0);   // (diagonal / 8)^2
+    // keys, sort, permutation
+    order_key_kernel<<<blocks, 256, 0, st>>>(n, nj, G.js, G.addr_of, G.ord, G.d_keys_tmp, G.d_vals_tmp);
+    CK(cudaGetLastError());
+    size_t need = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, need, G.d_keys_tmp, G.d_keys, G.d_vals_tmp, G.d_vals, n, 0, 32, st));
+    if (need > G.sort_tmp_bytes) {
+        CK(cudaStreamSynchronize(st));
+        if (G.d_sort_tmp) cudaFree(G.d_sort_tmp);
+        CK(cudaMalloc(&G.d_sort_tmp, need));
+        G.sort_tmp_bytes = need;
+    }
+    CK(cub::DeviceRadixSort::SortPairs(G.d_sort_tmp, need, G.d_keys_tmp, G.d_keys, G.d_vals_tmp, G.d_vals, n, 0, 32, st));
+    order_permute_kernel<<<blocks, 256, 0, st>>>(n, G.d_vals, G.js, G.addr_of, G.js2, G.addr_of2, G.js.slot_of);
+    CK(cudaGetLastError());
+    for (int k = 0; k < 7; k++) std::swap(G.js.q[k], G.js2.q[k]);
+    std::swap(G.js.ia, G.js2.ia);
+    std::swap(G.js.near2, G.js2.near2);
+    std::swap(G.addr_of, G.addr_of2);
+    // id -> slot table over the prefix
+    const int nprefix = std::min(nj, n);
+    unsigned size = 1024;
+    while (size < 2u * (unsigned)nprefix) size <<= 1;
+    if (size > G.hash_size) {
+        CK(cudaStreamSynchronize(st));
+        dev_free(G.d_hash);
+        dev_alloc(G.d_hash, size);
+        G.hash_size = size;
+    }
+    CK(cudaMemsetAsync(G.d_hash, 0, sizeof(u64) * size, st));
+    hash_insert_kernel<<<(nprefix + 255) / 256, 256, 0, st>>>(nprefix, G.js, G.d_hash, size - 1);
+    CK(cudaGetLastError());
+    G.ord.hash = G.d_hash;
+    G.ord.hash_mask = size - 1;
+    G.ord.keys = G.d_keys;
+    G.ord.nkeys = nprefix;
+    order_near_kernel<<<(nprefix + 255) / 256, 256, 0, st>>>(nprefix, G.js, G.near_w);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(G.h_slot_of.data(), G.js.slot_of, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    G.launches += 8;
+    G.j_dirty = true;       // slots moved and the origin changed: predict again
+    G.predicted_nj = -1;
+}
+
+// Does the next force call over [0, nj) need the order rebuilt first?  (called with the pending updates
+// counted but not necessarily flushed)
+bool order_stale(int nj)
+{
+    nj = std::min(nj, std::max(G.capacity, 0));
+    const bool stale = !G.order_valid || G.order_nj != nj || G.ids_dirty ||
+                       G.updates_since_force >= std::max<long long>(1, nj / 2) ||
+                       G.updates_since_order >= 4LL * std::max(nj, 1);
+    G.updates_since_force = 0;
+    return stale;
 }
 
 void ensure_partials(size_t records)
@@ -551,13 +721,31 @@ int choose_variant(int ni, int nj)
     return best;
 }
 
-// Launch the force kernel for i-block (iA,iB,iC) of ni particles against j in [0,nj).
-// inline_src != nullptr: HOST pointer to the packed i-block ([3][ni] float4, stride ni), carried in the
+// A packed i-block on the device: four float4 streams, the id-table result per particle, and (device
+// path) the index every packed particle's outputs go to.
+struct IBlock {
+    const float4 *A, *B, *C, *D;
+    int *conf;
+    const int *iperm;
+};
+IBlock iblock_of(float4 *base, size_t stride, int *conf, const int *iperm = nullptr)
+{
+    return IBlock{base, base + stride, base + 2 * stride, base + 3 * stride, conf, iperm};
+}
+
+template <int INL>
+void fill_inline(InlineI<INL> &ii, const float4 *src, int ni)
+{
+    for (int k = 0; k < 4; k++) memcpy(ii.d + INL * k, src + (size_t)ni * k, sizeof(float4) * ni);
+}
+
+// Launch the force kernel for the packed i-block ib of ni particles against j in [0,nj).
+// inline_src != nullptr: HOST pointer to the packed i-block ([4][ni] float4, stride ni), carried in the
 // kernel parameters (small i-blocks; masked kernels).  flag_seq != 0: outputs are host-mapped and the
 // launch raises G.h_flag = flag_seq when they are complete.
-void launch_force(int nj, int ni, const float4 *iA, const float4 *iB, const float4 *iC, float eps2, bool nn,
-                  bool list, double *out_sum, u64 *out_key, int *out_nnid, const float4 *inline_src = nullptr,
-                  unsigned long long flag_seq = 0, const HermiteArgs *herm = nullptr)
+void launch_force(int nj, int ni, const IBlock &ib, float eps2, bool nn, bool list, double *out_sum, u64 *out_key,
+                  int *out_nnid, const float4 *inline_src = nullptr, unsigned long long flag_seq = 0,
+                  const HermiteArgs *herm = nullptr)
 {
     if (nj > G.capacity - G.win_lo) nj = G.capacity - G.win_lo;
     int v = choose_variant(ni, nj);
@@ -580,36 +768,52 @@ void launch_force(int nj, int ni, const float4 *iA, const float4 *iB, const floa
     // c0 ~ fixed per-CTA cost (prologue + reduction) in tile units; w0 = 0.06 is measured: SMs do not
     // all run at the same speed, so one wave of long CTAs ends ~6 % later than four waves of short
     // ones that the hardware scheduler balances (profiles/r01_grid_granularity.txt).
+    // The search result only depends on (variant, i-blocks, tiles): the block-timestep regime asks for the
+    // same shape call after call, so the last answer is kept.
     const int slots = G.sm_count * vi.ctas_per_sm;
-    const double c0 = 1.5, w0 = 0.06;
-    int best_ns = 1;
-    double best_cost = 1e300;
-    int max_ns = std::min(ntiles, std::max(1, 4 * slots / n_iblocks));
-    for (int ns = 1; ns <= max_ns; ns++) {
-        int tps_ = (ntiles + ns - 1) / ns;
-        int ns_ = (ntiles + tps_ - 1) / tps_;
-        long long ctas = (long long)ns_ * n_iblocks;
-        long long waves = (ctas + slots - 1) / slots;
-        double cost = ((double)waves + w0) * (tps_ + c0);
-        if (cost < best_cost * 0.999) {
-            best_cost = cost;
-            best_ns = ns_;
+    static int memo_key[4] = {-1, -1, -1, -1}, memo_ns = 1;
+    int nsplit;
+    if (memo_key[0] == v && memo_key[1] == n_iblocks && memo_key[2] == ntiles && memo_key[3] == slots) {
+        nsplit = memo_ns;
+    } else {
+        const double c0 = 1.5, w0 = 0.06;
+        int best_ns = 1;
+        double best_cost = 1e300;
+        int max_ns = std::min(ntiles, std::max(1, 4 * slots / n_iblocks));
+        for (int ns = 1; ns <= max_ns; ns++) {
+            int tps_ = (ntiles + ns - 1) / ns;
+            int ns_ = (ntiles + tps_ - 1) / tps_;
+            long long ctas = (long long)ns_ * n_iblocks;
+            long long waves = (ctas + slots - 1) / slots;
+            double cost = ((double)waves + w0) * (tps_ + c0);
+            if (cost < best_cost * 0.999) {
+                best_cost = cost;
+                best_ns = ns_;
+            }
         }
+        nsplit = best_ns;
+        memo_key[0] = v; memo_key[1] = n_iblocks; memo_key[2] = ntiles; memo_key[3] = slots;
+        memo_ns = nsplit;
     }
-    int nsplit = best_ns;
     if (G.force_nsplit > 0) nsplit = std::min(G.force_nsplit, ntiles);   // G6_B200_NSPLIT: experiments only
     int tps = (ntiles + nsplit - 1) / nsplit;
     nsplit = (ntiles + tps - 1) / tps;
 
     ForceArgs a{};
-    // G.win_lo > 0: the launch works on the j-window [win_lo, win_lo + nj) of the local arrays (sharded
-    // Hermite step on a replicated state); win_lo is a multiple of TILE, so tiles keep their id ranges
-    a.jA = G.js.A + G.win_lo; a.jB = G.js.B + G.win_lo; a.jC = G.js.C + G.win_lo;
-    a.iA = iA; a.iB = iB; a.iC = iC;
+    // G.win_lo > 0: the launch works on the window [win_lo, win_lo + nj) of the slots (sharded Hermite
+    // step on a replicated state); win_lo is a multiple of TILE
+    a.jA = G.js.A + G.win_lo; a.jB = G.js.B + G.win_lo; a.jC = G.js.C + G.win_lo; a.jL = G.js.L + G.win_lo;
+    a.jG = G.js.gbb + (size_t)(G.win_lo / TILE) * TBOX;
+    a.iA = ib.A; a.iB = ib.B; a.iC = ib.C; a.iD = ib.D;
+    a.conf = ib.conf;
+    a.iperm = ib.iperm;
     a.ni = ni; a.nj = nj;
     a.tiles_per_split = tps; a.nsplit = nsplit;
     a.ni_pad = ni;
-    a.j_offset = G.j_offset + G.win_lo;
+    a.j_offset = G.j_offset;
+    a.slot0 = G.win_lo;
+    a.js = G.js;
+    a.ord = G.ord;
     // many splits of few i-blocks: sum the partials with a kernel of its own (one warp per i, spread
     // over the SMs) instead of the last CTA -- except for the 4-particle shape, whose last CTA puts
     // 32 lanes on each i
@@ -635,6 +839,12 @@ void launch_force(int nj, int ni, const float4 *iA, const float4 *iB, const floa
         a.flag_seq = flag_seq;
         a.done_expected = defer ? (unsigned)reduce_ctas : (unsigned)n_iblocks;
     }
+    if (v == V_F2 || v == V_F4) {
+        // pre-pass of the speculative kernel: id-table lookup and nearest-neighbour bound of every i-particle
+        near_kernel<<<(ni + 255) / 256, 256, 0, G.stream>>>(a, G.near_w);
+        CK(cudaGetLastError());
+        G.launches++;
+    }
     if (herm) {
         a.herm = *herm;
         if (v == V_T1) launch_herm<1, 4, false, 2>(a, grid, G.stream);
@@ -643,13 +853,13 @@ void launch_force(int nj, int ni, const float4 *iA, const float4 *iB, const floa
     } else if (inline_src) {
         if (ni <= 64) {
             InlineI<64> ii;
-            for (int k = 0; k < 3; k++) memcpy(ii.d + 64 * k, inline_src + (size_t)ni * k, sizeof(float4) * ni);
+            fill_inline(ii, inline_src, ni);
             if (v == V_T1) launch_inline<1, 4, false, 2, 64>(a, grid, ii, G.stream);
             else if (v == V_W1) launch_inline<1, 32, false, 2, 64>(a, grid, ii, G.stream);
             else launch_inline<2, 32, true, 2, 64>(a, grid, ii, G.stream);
         } else {
             InlineI<384> ii;
-            for (int k = 0; k < 3; k++) memcpy(ii.d + 384 * k, inline_src + (size_t)ni * k, sizeof(float4) * ni);
+            fill_inline(ii, inline_src, ni);
             if (v == V_T1) launch_inline<1, 4, false, 2, 384>(a, grid, ii, G.stream);
             else if (v == V_W1) launch_inline<1, 32, false, 2, 384>(a, grid, ii, G.stream);
             else launch_inline<2, 32, true, 2, 384>(a, grid, ii, G.stream);
@@ -678,10 +888,26 @@ void launch_force(int nj, int ni, const float4 *iA, const float4 *iB, const floa
     }
 }
 
+bool is_fast_variant(int v) { return v == V_F2 || v == V_F4; }
+
 void free_all()
 {
-    for (int k = 0; k < 7; k++) dev_free(G.js.q[k]);
-    dev_free(G.js.A); dev_free(G.js.B); dev_free(G.js.C);
+    for (int k = 0; k < 7; k++) { dev_free(G.js.q[k]); dev_free(G.js2.q[k]); }
+    dev_free(G.js.ia); dev_free(G.js2.ia); dev_free(G.js.near2); dev_free(G.js2.near2);
+    dev_free(G.js.A); dev_free(G.js.B); dev_free(G.js.C); dev_free(G.js.L); dev_free(G.js.gbb);
+    dev_free(G.js.slot_of); dev_free(G.addr_of); dev_free(G.addr_of2);
+    dev_free(G.d_keys); dev_free(G.d_keys_tmp); dev_free(G.d_vals); dev_free(G.d_vals_tmp);
+    if (G.d_sort_tmp) cudaFree(G.d_sort_tmp);
+    G.d_sort_tmp = nullptr; G.sort_tmp_bytes = 0;
+    dev_free(G.d_box); host_free(G.h_box);
+    dev_free(G.d_hash); G.hash_size = 0;
+    G.ord = OrderInfo{};
+    G.order_valid = false; G.order_nj = -1; G.ids_dirty = false;
+    G.updates_since_order = G.updates_since_force = 0;
+    G.h_slot_of.clear(); G.h_id.clear(); G.h_perm.clear();
+    dev_free(G.d_conf); dev_free(G.d_conf2);
+    dev_free(G.d_ikey); dev_free(G.d_ikey_tmp); dev_free(G.d_iperm); dev_free(G.d_iperm_tmp);
+    G.isort_cap = 0;
     dev_free(G.d_up);
     for (int b = 0; b < 2; b++) {
         host_free(G.h_up2[b]);
@@ -698,7 +924,7 @@ void free_all()
         Context::Hermite &H = G.herm;
         host_free(H.h_ilist); host_free(H.h_olddt); host_free(H.h_outdt); host_free(H.h_outpot); host_free(H.h_outnn);
         dev_free(H.d_pred); dev_free(H.d_i); dev_free(H.d_sum); dev_free(H.d_key); dev_free(H.d_nnid);
-        dev_free(H.d_ilist); dev_free(H.d_olddt);
+        dev_free(H.d_ilist); dev_free(H.d_olddt); dev_free(H.d_conf);
         H.cap = 0;
         H.time.clear(); H.dt.clear();
         H.initialised = false;
@@ -711,26 +937,26 @@ void free_all()
     dev_free(G.d_sum2); dev_free(G.d_key2); dev_free(G.d_nnid2);
     host_free(G.h_ngb_cnt); host_free(G.h_ngb_list);
     G.capacity = 0; G.nj_hi = 0; G.up_cap = 0; G.up_n = 0; G.part_records = 0; G.i2_cap = 0;
-    G.slot_of_addr.clear();
+    G.pending_of_addr.clear();
     G.predicted_nj = -1; G.j_dirty = false; G.pending = false;
     G.ngb_valid = G.ngb_built = G.ngb_fetched = false;
 }
 
 void stage_j(int address, int index, double tj, double mass, const double *j6, const double *a2, const double *v,
-             const double *x)
+             const double *x, int key_address = -1)
 {
     if (address < 0) {
         fprintf(stderr, "g6_b200: FATAL g6_set_j_particle address %d < 0\n", address);
         exit(-1);
     }
     ensure_capacity(address + 1);
-    int slot = G.slot_of_addr[address];
-    if (slot < 0) {  // last write wins within a batch (sapporo.cpp:83-110)
+    int pos = G.pending_of_addr[address];
+    if (pos < 0) {  // last write wins within a batch (sapporo.cpp:83-110)
         ensure_up_cap(G.up_n + 1);
-        slot = G.up_n++;
-        G.slot_of_addr[address] = slot;
+        pos = G.up_n++;
+        G.pending_of_addr[address] = pos;
     }
-    JUpdate &u = G.h_up[slot];
+    JUpdate &u = G.h_up[pos];
     for (int k = 0; k < 3; k++) {
         u.x[k] = x[k];
         u.v[k] = v[k];
@@ -738,10 +964,17 @@ void stage_j(int address, int index, double tj, double mass, const double *j6, c
         u.j[k] = 6.0 * j6[k];   // j6 = jerk/6  (sapporo.cpp:95)
     }
     u.t = tj;
-    u.m = (float)mass;
+    u.m = mass;
     u.id = index;
+    u.slot = G.h_slot_of[address];
+    u.kaddr = key_address >= 0 ? key_address : address;
     u.addr = address;
-    u.pad[0] = u.pad[1] = u.pad[2] = 0;
+    if (G.h_id[address] != index) {   // a new particle or a new id at this address: the id table is out of date
+        G.h_id[address] = index;
+        G.ids_dirty = true;
+    }
+    G.updates_since_order++;
+    G.updates_since_force++;
     if (address + 1 > G.nj_hi) G.nj_hi = address + 1;
     // big batches (the caller is sending back a large block, or loading the system) go out while the
     // caller is still staging the rest, so the next force call does not start with a multi-MB upload
@@ -783,26 +1016,46 @@ int get_device_count(void)
     return n;
 }
 
-int g6_open_(int *id)
+// ---- multi-device layer ----------------------------------------------------------------------------
+// G6_B200_DEVICES = n > 1 (or "all"): g6_open_ opens n devices in this one process and drives them as ONE
+// j-memory -- the device-side form of ph4's MPI mode (gpu.cc:40,56-59 + idata.cc:284-313) without MPI:
+// j-addresses are dealt out in chunks of 256 (address / 256 mod n owns it, so every device holds a uniform
+// sample of the system and any prefix [0, nj) is a prefix on every device), g6_set_j_particle_ goes to the
+// owner, g6calc_firsthalf_ sends the packed i-block to all devices and launches the force kernels, which
+// store their partial sums into device 0's exchange buffer over NVLink (peer access enabled directly), and
+// device 0 combines them (sum, min key, id of the winner) for g6calc_lasthalf_.
+struct Multi {
+    int n = 0;           // devices open (0: library closed)
+    int dev_now = -1;    // device the CUDA runtime currently has selected
+} M;
+
+static void use(int k)
 {
-    int ndev = get_device_count();
-    if (ndev <= 0) {
-        fprintf(stderr, "g6_b200: FATAL no CUDA device found (this library has no CPU fallback)\n");
-        exit(-1);
+    g_cur = &g_ctx[k];
+    if (M.dev_now != G.device) {
+        CK(cudaSetDevice(G.device));
+        M.dev_now = G.device;
     }
-    int dev = id ? *id : 0;
-    if (env_int("G6_B200_DEVICE_MODULO", 0)) dev = ((dev % ndev) + ndev) % ndev;
-    if (dev < 0 || dev >= ndev) {
-        fprintf(stderr, "g6_b200: g6_open: no CUDA device with id %d (%d present)\n", dev, ndev);
-        return -1;
-    }
-    if (G.open) {
-        if (dev == G.device) return 0;
-        int d = G.device;
-        g6_close_(&d);
-    }
+}
+static inline int owner_of(int address) { return M.n > 1 ? (address / TILE) % M.n : 0; }
+static inline int local_address(int address)
+{
+    return M.n > 1 ? (address / (TILE * M.n)) * TILE + address % TILE : address;
+}
+// addresses of [0, nj) that device k owns form the prefix [0, local_count) of its local addresses
+static inline int local_count(int nj, int k)
+{
+    if (M.n <= 1) return nj;
+    const int cycle = TILE * M.n;
+    const int rem = nj % cycle - k * TILE;
+    return (nj / cycle) * TILE + std::max(0, std::min(TILE, rem));
+}
+
+static void open_context(int dev)   // g_cur selected by the caller
+{
     G.device = dev;
     CK(cudaSetDevice(dev));
+    M.dev_now = dev;
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, dev));
     if (prop.major < 10) {
@@ -818,9 +1071,18 @@ int g6_open_(int *id)
     G.variant = env_int("G6_B200_VARIANT", V_AUTO);
     G.refine = env_int("G6_B200_REFINE", 1);
     G.force_nsplit = env_int("G6_B200_NSPLIT", 0);
-    host_alloc(G.h_i, (size_t)3 * G.npipes);
-    dev_alloc(G.d_i, (size_t)3 * G.npipes);
-    dev_alloc(G.d_i2, (size_t)3 * G.npipes);
+    {
+        const char *e = getenv("G6_B200_KCLOSE");
+        G.kclose = (e && *e) ? (float)atof(e) : 16.f;
+        e = getenv("G6_B200_FARC");
+        G.farc = (e && *e) ? (float)atof(e) : 0.125f;
+        G.near_w = std::max(1, env_int("G6_B200_NEAR_WINDOW", 32));
+    }
+    host_alloc(G.h_i, (size_t)4 * G.npipes);
+    dev_alloc(G.d_i, (size_t)4 * G.npipes);
+    dev_alloc(G.d_conf, (size_t)G.npipes);
+    dev_alloc(G.d_i2, (size_t)4 * G.npipes);
+    dev_alloc(G.d_conf2, (size_t)G.npipes);
     G.i2_cap = G.npipes;
     dev_alloc(G.d_sum, (size_t)8 * G.npipes);    // [7n doubles][n ints] per i-block
     dev_alloc(G.d_key, (size_t)G.npipes);
@@ -848,33 +1110,86 @@ int g6_open_(int *id)
     G.open = true;
     if (env_int("G6_B200_VERBOSE", 0))
         fprintf(stderr, "g6_b200: open device %d (%s, %d SMs), npipes %d\n", dev, prop.name, G.sm_count, G.npipes);
+}
+
+static void close_context()
+{
+    if (!G.open) return;
+    CK(cudaSetDevice(G.device));
+    M.dev_now = G.device;
+    CK(cudaStreamSynchronize(G.stream));
+    g6x_peer_detach();
+    if (G.trace && G.tr_calls)
+        fprintf(stderr,
+                "g6_b200 trace: %lld force calls; mean us per call: flush %.2f predict %.2f pack %.2f h2d %.2f "
+                "launch %.2f d2h-issue %.2f wait %.2f unpack %.2f; %lld order rebuilds\n",
+                G.tr_calls, 1e6 * G.tr[0] / G.tr_calls, 1e6 * G.tr[1] / G.tr_calls, 1e6 * G.tr[2] / G.tr_calls,
+                1e6 * G.tr[3] / G.tr_calls, 1e6 * G.tr[4] / G.tr_calls, 1e6 * G.tr[5] / G.tr_calls,
+                1e6 * G.tr[6] / G.tr_calls, 1e6 * G.tr[7] / G.tr_calls, G.order_rebuilds);
+    free_all();
+    if (G.own_stream) cudaStreamDestroy(G.own_stream);
+    G.own_stream = G.stream = nullptr;
+    G.open = false;
+}
+
+static void peer_group_setup();   // below, with the exchange helpers
+
+int g6_open_(int *id)
+{
+    int ndev = get_device_count();
+    if (ndev <= 0) {
+        fprintf(stderr, "g6_b200: FATAL no CUDA device found (this library has no CPU fallback)\n");
+        exit(-1);
+    }
+    int dev = id ? *id : 0;
+    if (dev < 0 || dev >= ndev) {
+        // ph4's standalone driver passes an uninitialised gpu_id (jdata.h:137-170) and Fortran callers ignore
+        // the return value: fold the id onto the devices that exist instead of failing.  G6_B200_STRICT_DEVICE=1
+        // restores the reference's answer (sapporo.cpp:31-34: -1 for a bad id).
+        if (env_int("G6_B200_STRICT_DEVICE", 0)) {
+            fprintf(stderr, "g6_b200: g6_open: no CUDA device with id %d (%d present)\n", dev, ndev);
+            return -1;
+        }
+        const int folded = ((dev % ndev) + ndev) % ndev;
+        fprintf(stderr, "g6_b200: g6_open: no CUDA device with id %d (%d present): using device %d\n", dev, ndev, folded);
+        dev = folded;
+    }
+    int want = 1;
+    {
+        const char *e = getenv("G6_B200_DEVICES");
+        if (e && *e) want = (strcmp(e, "all") == 0) ? ndev : atoi(e);
+        want = std::max(1, std::min(want, std::min(ndev, MAX_DEVICES)));
+    }
+    if (M.n > 0) {
+        if (M.n == want && g_ctx[0].device == dev) return 0;
+        int d = g_ctx[0].device;
+        g6_close_(&d);
+    }
+    for (int k = 0; k < want; k++) {
+        g_cur = &g_ctx[k];
+        open_context((dev + k) % ndev);
+    }
+    M.n = want;
+    if (want > 1) peer_group_setup();
+    use(0);
     return 0;
 }
 
 int g6_close_(int *id)
 {
     (void)id;
-    if (!G.open) return 0;
-    CK(cudaSetDevice(G.device));
-    CK(cudaStreamSynchronize(G.stream));
-    g6x_peer_detach();
-    if (G.trace && G.tr_calls)
-        fprintf(stderr,
-                "g6_b200 trace: %lld force calls; mean us per call: flush %.2f predict %.2f pack %.2f h2d %.2f "
-                "launch %.2f d2h-issue %.2f wait %.2f unpack %.2f\n",
-                G.tr_calls, 1e6 * G.tr[0] / G.tr_calls, 1e6 * G.tr[1] / G.tr_calls, 1e6 * G.tr[2] / G.tr_calls,
-                1e6 * G.tr[3] / G.tr_calls, 1e6 * G.tr[4] / G.tr_calls, 1e6 * G.tr[5] / G.tr_calls,
-                1e6 * G.tr[6] / G.tr_calls, 1e6 * G.tr[7] / G.tr_calls);
-    free_all();
-    if (G.own_stream) cudaStreamDestroy(G.own_stream);
-    G.own_stream = G.stream = nullptr;
-    G.open = false;
+    for (int k = 0; k < M.n; k++) {
+        g_cur = &g_ctx[k];
+        close_context();
+    }
+    M.n = 0;
+    g_cur = &g_ctx[0];
     return 0;
 }
 
 int g6_npipes_(void)
 {
-    if (G.open) return G.npipes;
+    if (g_ctx[0].open) return g_ctx[0].npipes;
     return std::max(1, env_int("G6_B200_NPIPES", 16384));
 }
 
@@ -885,7 +1200,7 @@ int g6_set_ti_(int *id, double *ti)
 {
     (void)id;
     require_open("g6_set_ti_");
-    G.ti = *ti;
+    for (int k = 0; k < std::max(1, M.n); k++) g_ctx[k].ti = *ti;
     return 0;
 }
 
@@ -894,67 +1209,174 @@ int g6_set_j_particle_(int *cluster_id, int *address, int *index, double *tj, do
 {
     (void)cluster_id; (void)dtj; (void)k18;
     require_open("g6_set_j_particle_");
+    if (M.n > 1) {
+        if (*address < 0) {
+            fprintf(stderr, "g6_b200: FATAL g6_set_j_particle address %d < 0\n", *address);
+            exit(-1);
+        }
+        use(owner_of(*address));
+        stage_j(local_address(*address), *index, *tj, *mass, j6, a2, v, x, *address);
+        return 0;
+    }
     stage_j(*address, *index, *tj, *mass, j6, a2, v, x);
     return 0;
 }
+
+// Morton order of an i-block on the host (radix sort, 3 passes of 10 bits): G.h_perm[k] = caller index of
+// the particle at packed position k.  xi are the caller's coordinates.
+static void host_morton_perm(int n, double xi[][3])
+{
+    const OrderInfo &o = G.ord;
+    G.h_perm.resize(n);
+    G.h_perm2.resize(n);
+    G.h_ikey.resize(n);
+    G.h_ikey2.resize(n);
+    auto spread = [](unsigned v) {
+        v = (v | (v << 16)) & 0x030000ffu;
+        v = (v | (v << 8)) & 0x0300f00fu;
+        v = (v | (v << 4)) & 0x030c30c3u;
+        v = (v | (v << 2)) & 0x09249249u;
+        return v;
+    };
+    for (int i = 0; i < n; i++) {
+        unsigned c[3];
+        for (int d = 0; d < 3; d++) {
+            float f = ((float)(xi[i][d] - G.js.x0[d]) - o.blo[d]) * o.binv[d];
+            f = std::min(std::max(f, 0.f), 1023.f);
+            c[d] = (unsigned)f;
+        }
+        G.h_ikey[i] = spread(c[0]) | (spread(c[1]) << 1) | (spread(c[2]) << 2);
+        G.h_perm[i] = i;
+    }
+    unsigned *ka = G.h_ikey.data(), *kb = G.h_ikey2.data();
+    int *va = G.h_perm.data(), *vb = G.h_perm2.data();
+    for (int pass = 0; pass < 3; pass++) {
+        unsigned cnt[1025] = {0};
+        const int sh = 10 * pass;
+        for (int i = 0; i < n; i++) cnt[((ka[i] >> sh) & 1023u) + 1]++;
+        for (int b = 0; b < 1024; b++) cnt[b + 1] += cnt[b];
+        for (int i = 0; i < n; i++) {
+            const unsigned pos = cnt[(ka[i] >> sh) & 1023u]++;
+            kb[pos] = ka[i];
+            vb[pos] = va[i];
+        }
+        std::swap(ka, kb);
+        std::swap(va, vb);
+    }
+    if (va != G.h_perm.data()) G.h_perm.swap(G.h_perm2);   // three passes: the result sits in the second pair
+}
+
+struct ExchangeSlots;
+static void gather_begin_all(int ni);
+static void gather_launch(int k, int nj, int ni, const IBlock &ib, float eps2, double *out_sum, u64 *out_key,
+                          int *out_nnid, const float4 *inline_src, unsigned long long flag_seq);
+static void gather_finish_all(int ni, bool direct);
 
 void g6calc_firsthalf_(int *cluster_id, int *nj, int *ni, int index[], double xi[][3], double vi[][3],
                        double aold[][3], double j6old[][3], double phiold[], double *eps2, double h2[])
 {
     (void)cluster_id; (void)aold; (void)j6old; (void)phiold;
     require_open("g6calc_firsthalf_");
+    const int nd = std::max(1, M.n);
+    use(0);
+    Context &R = g_ctx[0];   // root: holds the packed i-block and receives the results
     int n = *ni;
-    if (n > G.npipes || n < 0) {
-        fprintf(stderr, "g6_b200: FATAL g6calc_firsthalf ni = %d exceeds g6_npipes() = %d\n", n, G.npipes);
+    if (n > R.npipes || n < 0) {
+        fprintf(stderr, "g6_b200: FATAL g6calc_firsthalf ni = %d exceeds g6_npipes() = %d\n", n, R.npipes);
         exit(-1);
     }
-    if (G.pending) CK(cudaStreamSynchronize(G.stream));  // a firsthalf without its lasthalf
+    if (R.pending)
+        for (int k = 0; k < nd; k++) {   // a firsthalf without its lasthalf
+            use(k);
+            CK(cudaStreamSynchronize(G.stream));
+        }
+    use(0);
     double t0 = G.trace ? wall() : 0.0, t1 = 0.0;
-    // scatter (small batches: fused with the predictor, records read from mapped pinned memory) + predict
-    const bool inl = (n > 0) && (n <= G.inline_max) && (G.variant == V_AUTO);
-    predict_with_updates(*nj);
+    // scatter (small batches: fused with the predictor, records read from mapped pinned memory) + predict;
+    // the Morton order of the j-memory is rebuilt first when a bulk load or new ids made it stale (all devices
+    // together: they share the origin the i-block is packed against)
+    bool stale = false;
+    for (int k = 0; k < nd; k++) {
+        g_cur = &g_ctx[k];
+        stale |= order_stale(local_count(*nj, k));
+    }
+    for (int k = 0; k < nd; k++) {
+        use(k);
+        if (stale) {
+            flush_updates();
+            rebuild_order(local_count(*nj, k));
+        }
+        predict_with_updates(local_count(*nj, k));
+    }
+    use(0);
     G6_TR(0)
     G6_TR(1)
-    // pack the i-block: double -> double-single (sapporo.cpp:125-134); the three float4 streams are
-    // laid out back to back with stride n, so that they cross PCIe in ONE copy
-    float4 *A = G.h_i, *B = G.h_i + n, *C = G.h_i + 2 * (size_t)n;
+    const bool inl = (n > 0) && (n <= G.inline_max) && (G.variant == V_AUTO);
+    // Morton-sort the block when it goes to the speculative kernel (whose warps want 64 neighbouring particles)
+    const bool sorted = (n > 1) && is_fast_variant(choose_variant(n, std::min(local_count(*nj, 0), G.capacity))) &&
+                        G.ord.nkeys > 0;
+    if (sorted) host_morton_perm(n, xi); else G.h_perm.clear();
+    // pack the i-block: double -> double-single relative to the origin (sapporo.cpp:125-134); the four
+    // float4 streams are laid out back to back with stride n, so that they cross PCIe in ONE copy
+    float4 *A = G.h_i, *B = G.h_i + n, *C = G.h_i + 2 * (size_t)n, *D = G.h_i + 3 * (size_t)n;
     bool any_h2 = false;
-    for (int i = 0; i < n; i++) {
-        double x = xi[i][0], y = xi[i][1], z = xi[i][2];
+    const double ox = G.js.x0[0], oy = G.js.x0[1], oz = G.js.x0[2];
+    for (int k = 0; k < n; k++) {
+        const int i = sorted ? G.h_perm[k] : k;
+        double x = xi[i][0] - ox, y = xi[i][1] - oy, z = xi[i][2] - oz;
         float xh = (float)x, yh = (float)y, zh = (float)z;
+        float vxh = (float)vi[i][0], vyh = (float)vi[i][1], vzh = (float)vi[i][2];
         float hh = h2 ? (float)h2[i] : 0.f;
         any_h2 |= (hh > 0.f);
-        A[i] = make_float4(xh, yh, zh, hh);
+        A[k] = make_float4(xh, yh, zh, hh);
         union { int i; float f; } cv;
         cv.i = index[i];
-        B[i] = make_float4((float)(x - (double)xh), (float)(y - (double)yh), (float)(z - (double)zh), cv.f);
-        C[i] = make_float4((float)vi[i][0], (float)vi[i][1], (float)vi[i][2], 0.f);
+        B[k] = make_float4((float)(x - (double)xh), (float)(y - (double)yh), (float)(z - (double)zh), cv.f);
+        C[k] = make_float4(vxh, vyh, vzh, 0.f);
+        D[k] = make_float4((float)(vi[i][0] - (double)vxh), (float)(vi[i][1] - (double)vyh),
+                           (float)(vi[i][2] - (double)vzh), 0.f);
     }
     G6_TR(2)
     // small i-blocks travel in the kernel parameters (no H2D copy); their results are written by the
     // kernel into mapped host memory and announced by a flag (no D2H copy, no stream synchronisation)
     const bool direct = (n > 0) && (n <= G.direct_max);
-    if (n > 0 && !inl) CK(cudaMemcpyAsync(G.d_i, G.h_i, sizeof(float4) * 3 * (size_t)n, cudaMemcpyHostToDevice, G.stream));
-    G.i_on_device = !inl;
-    G.cur_direct = direct;
-    G6_TR(3)
-    G.cur_ni = n;
-    G.cur_nj = *nj;
-    G.cur_eps2 = (float)*eps2;
-    G.cur_any_h2 = any_h2;
-    G.pending = true;
-    G.ngb_valid = G.ngb_fetched = false;
+    R.i_on_device = !inl;
+    R.cur_direct = direct;
+    R.cur_ni = n;
+    R.cur_nj = *nj;
+    R.cur_eps2 = (float)*eps2;
+    R.cur_any_h2 = any_h2;
+    R.pending = true;
+    R.ngb_valid = R.ngb_fetched = false;
     // The force kernel starts here, asynchronously (GRAPE's firsthalf/lasthalf split exists for this
     // overlap): always with the nearest-neighbour search, which costs ~1 % and is simply not copied
     // back by g6calc_lasthalf_.  Neighbour-sphere lists are NOT built here: ph4 and phiGRAPE pass
     // h2 = eps2 on every call (gpu.cc:266,324; gravity.F:72) and never read the lists, so they are
     // built on demand by g6_read_neighbour_list_.
     // outputs: [7n doubles][n ints] back to back, so that they come back in ONE copy
-    if (n > 0) {
+    if (n > 0 && nd == 1) {
+        if (!inl) CK(cudaMemcpyAsync(G.d_i, G.h_i, sizeof(float4) * 4 * (size_t)n, cudaMemcpyHostToDevice, G.stream));
+        G6_TR(3)
         double *out = direct ? G.dev_h_sum : G.d_sum;
-        launch_force(G.cur_nj, n, G.d_i, G.d_i + n, G.d_i + 2 * (size_t)n, G.cur_eps2, true, false, out, G.d_key,
+        launch_force(R.cur_nj, n, iblock_of(G.d_i, n, G.d_conf), R.cur_eps2, true, false, out, G.d_key,
                      reinterpret_cast<int *>(out + 7 * (size_t)n), inl ? G.h_i : nullptr,
                      direct ? ++G.flag_seq : 0ull);
+    } else if (n > 0) {
+        // every device gets the block (from the root's pinned copy) and sums over its own j; the partials meet
+        // in the root's exchange buffer, where the root's combine kernel writes the totals (and raises the flag)
+        gather_begin_all(n);
+        const unsigned long long seq = direct ? ++R.flag_seq : 0ull;
+        for (int k = 0; k < nd; k++) {
+            use(k);
+            if (!inl) CK(cudaMemcpyAsync(G.d_i, R.h_i, sizeof(float4) * 4 * (size_t)n, cudaMemcpyHostToDevice, G.stream));
+            gather_launch(k, local_count(*nj, k), n, iblock_of(G.d_i, n, G.d_conf), R.cur_eps2, nullptr, nullptr, nullptr,
+                          inl ? R.h_i : nullptr, 0ull);
+            G.i_on_device = !inl;
+        }
+        (void)seq;
+        gather_finish_all(n, direct);
+        use(0);
+        G6_TR(3)
     }
     G6_TR(4)
     if (G.trace) G.tr_calls++;
@@ -963,6 +1385,7 @@ void g6calc_firsthalf_(int *cluster_id, int *nj, int *ni, int index[], double xi
 static int lasthalf_common(int nj, int ni, double acc[][3], double jerk[][3], double pot[], int *inn)
 {
     require_open("g6calc_lasthalf_");
+    use(0);
     if (!G.pending || ni != G.cur_ni) {
         fprintf(stderr, "g6_b200: FATAL g6calc_lasthalf without matching g6calc_firsthalf (ni %d vs %d)\n", ni,
                 G.cur_ni);
@@ -983,12 +1406,14 @@ static int lasthalf_common(int nj, int ni, double acc[][3], double jerk[][3], do
             G6_TR(6)
         }
         const int *h_nnid = reinterpret_cast<const int *>(G.h_sum + 7 * (size_t)ni);
-        for (int i = 0; i < ni; i++) {
-            const double *s = G.h_sum + (size_t)7 * i;
+        const bool sorted = !G.h_perm.empty();
+        for (int k = 0; k < ni; k++) {
+            const int i = sorted ? G.h_perm[k] : k;
+            const double *s = G.h_sum + (size_t)7 * k;
             acc[i][0] = s[0]; acc[i][1] = s[1]; acc[i][2] = s[2];
             jerk[i][0] = s[3]; jerk[i][1] = s[4]; jerk[i][2] = s[5];
             pot[i] = -s[6];
-            if (nn) inn[i] = h_nnid[i];
+            if (nn) inn[i] = h_nnid[k];
         }
         G6_TR(7)
     }
@@ -1018,44 +1443,69 @@ int g6_flush_jp_buffer_(int *cluster_id) { (void)cluster_id; return 0; }
 int g6_reset_(int *cluster_id) { (void)cluster_id; return 0; }
 int g6_reset_fofpga_(int *cluster_id) { (void)cluster_id; return 0; }
 
+// second pass over the captured i-block on the current device (still in d_i; j state unchanged since its
+// lasthalf2) with the list-building variant of the masked kernel; forces go to scratch
+static void build_lists_here(int nj_local, int ni, float eps2)
+{
+    if (!G.d_ngb_cnt) {
+        dev_alloc(G.d_ngb_cnt, (size_t)G.npipes);
+        dev_alloc(G.d_ngb_list, (size_t)G.npipes * G.ngb_cap);
+        host_alloc(G.h_ngb_cnt, (size_t)G.npipes);
+        host_alloc(G.h_ngb_list, (size_t)G.npipes * G.ngb_cap);
+        dev_alloc(G.d_sum2, (size_t)7 * G.npipes);
+        dev_alloc(G.d_key2, (size_t)G.npipes);
+        dev_alloc(G.d_nnid2, (size_t)G.npipes);
+    }
+    if (!G.i_on_device) {   // the block went out in the kernel parameters: d_i was never written
+        CK(cudaMemcpyAsync(G.d_i, g_ctx[0].h_i, sizeof(float4) * 4 * (size_t)ni, cudaMemcpyHostToDevice, G.stream));
+        G.i_on_device = true;
+    }
+    CK(cudaMemsetAsync(G.d_ngb_cnt, 0, sizeof(int) * ni, G.stream));
+    launch_force(nj_local, ni, iblock_of(G.d_i, ni, G.d_conf), eps2, true, true, G.d_sum2, G.d_key2, G.d_nnid2);
+}
+
 int g6_read_neighbour_list_(int *cluster_id)
 {
     (void)cluster_id;
     require_open("g6_read_neighbour_list_");
-    if (!G.ngb_valid) {
-        G.ngb_fetched = false;
+    Context &R = g_ctx[0];
+    if (!R.ngb_valid) {
+        R.ngb_fetched = false;
         return 0;  // no lists were requested (all h2 <= 0 or lasthalf without nn)
     }
-    int ni = G.cur_ni;
-    if (!G.ngb_built) {
-        // second pass over the captured i-block (still in d_i; j state unchanged since its lasthalf2)
-        // with the list-building variant of the masked kernel; forces go to scratch
-        if (!G.d_ngb_cnt) {
-            dev_alloc(G.d_ngb_cnt, (size_t)G.npipes);
-            dev_alloc(G.d_ngb_list, (size_t)G.npipes * G.ngb_cap);
-            host_alloc(G.h_ngb_cnt, (size_t)G.npipes);
-            host_alloc(G.h_ngb_list, (size_t)G.npipes * G.ngb_cap);
-            dev_alloc(G.d_sum2, (size_t)7 * G.npipes);
-            dev_alloc(G.d_key2, (size_t)G.npipes);
-            dev_alloc(G.d_nnid2, (size_t)G.npipes);
+    const int nd = std::max(1, M.n);
+    const int ni = R.cur_ni;
+    if (!R.ngb_built) {
+        for (int k = 0; k < nd; k++) {
+            use(k);
+            build_lists_here(local_count(R.cur_nj, k), ni, R.cur_eps2);
         }
-        if (!G.i_on_device) {   // the block went out in the kernel parameters: d_i was never written
-            CK(cudaMemcpyAsync(G.d_i, G.h_i, sizeof(float4) * 3 * (size_t)ni, cudaMemcpyHostToDevice, G.stream));
-            G.i_on_device = true;
-        }
-        CK(cudaMemsetAsync(G.d_ngb_cnt, 0, sizeof(int) * ni, G.stream));
-        launch_force(G.cur_nj, ni, G.d_i, G.d_i + ni, G.d_i + 2 * (size_t)ni, G.cur_eps2, true, true, G.d_sum2,
-                     G.d_key2, G.d_nnid2);
-        G.ngb_built = true;
+        R.ngb_built = true;
     }
-    CK(cudaMemcpyAsync(G.h_ngb_cnt, G.d_ngb_cnt, sizeof(int) * ni, cudaMemcpyDeviceToHost, G.stream));
-    CK(cudaMemcpyAsync(G.h_ngb_list, G.d_ngb_list, sizeof(int) * (size_t)ni * G.ngb_cap, cudaMemcpyDeviceToHost,
-                       G.stream));
-    CK(cudaStreamSynchronize(G.stream));
-    G.ngb_fetched = true;
+    for (int k = 0; k < nd; k++) {
+        use(k);
+        CK(cudaMemcpyAsync(G.h_ngb_cnt, G.d_ngb_cnt, sizeof(int) * ni, cudaMemcpyDeviceToHost, G.stream));
+        CK(cudaMemcpyAsync(G.h_ngb_list, G.d_ngb_list, sizeof(int) * (size_t)ni * G.ngb_cap, cudaMemcpyDeviceToHost,
+                           G.stream));
+    }
+    for (int k = 0; k < nd; k++) {
+        use(k);
+        CK(cudaStreamSynchronize(G.stream));
+    }
+    use(0);
+    R.ngb_fetched = true;
+    // caller index -> packed position (the block may have been Morton-sorted)
+    R.h_perm2.assign(ni, 0);
+    for (int k = 0; k < ni; k++) R.h_perm2[R.h_perm.empty() ? k : R.h_perm[k]] = k;
     int overflow = 0;
-    for (int i = 0; i < ni; i++)
-        if (G.h_ngb_cnt[i] > G.ngb_cap) overflow = 1;
+    for (int i = 0; i < ni; i++) {
+        long long tot = 0;
+        for (int k = 0; k < nd; k++) {
+            tot += g_ctx[k].h_ngb_cnt[i];
+            if (g_ctx[k].h_ngb_cnt[i] > g_ctx[k].ngb_cap) overflow = 1;
+        }
+        if (tot > R.ngb_cap) overflow = 1;
+    }
     return overflow;
 }
 
@@ -1063,23 +1513,37 @@ int g6_get_neighbour_list_(int *cluster_id, int *ipipe, int *maxlength, int *n_n
 {
     (void)cluster_id;
     require_open("g6_get_neighbour_list_");
+    Context &R = g_ctx[0];
     int ip = *ipipe;
-    if (ip < 0 || ip >= G.cur_ni) {
-        fprintf(stderr, "g6_b200: FATAL g6_get_neighbour_list ipipe = %d >= ni = %d\n", ip, G.cur_ni);
+    if (ip < 0 || ip >= R.cur_ni) {
+        fprintf(stderr, "g6_b200: FATAL g6_get_neighbour_list ipipe = %d >= ni = %d\n", ip, R.cur_ni);
         exit(-1);  // as sapporo.cpp:254-258
     }
-    if (!G.ngb_valid || !G.ngb_fetched) {
+    if (!R.ngb_valid || !R.ngb_fetched) {
         *n_neighbours = 0;
         return 0;
     }
-    int cnt = G.h_ngb_cnt[ip];
-    int have = std::min(cnt, G.ngb_cap);
-    int *src = G.h_ngb_list + (size_t)ip * G.ngb_cap;
-    std::sort(src, src + have);
-    int ncopy = std::min(have, *maxlength);
-    memcpy(neighbour_list, src, sizeof(int) * ncopy);
-    *n_neighbours = cnt;
-    return (cnt > *maxlength || cnt > G.ngb_cap) ? 1 : 0;
+    const int nd = std::max(1, M.n);
+    const int pos = R.h_perm2[ip];
+    static std::vector<int> merged;
+    merged.clear();
+    long long cnt = 0;
+    bool truncated = false;
+    for (int k = 0; k < nd; k++) {
+        const Context &c = g_ctx[k];
+        const int ck = c.h_ngb_cnt[pos];
+        const int have = std::min(ck, c.ngb_cap);
+        truncated |= (ck > c.ngb_cap);
+        cnt += ck;
+        merged.insert(merged.end(), c.h_ngb_list + (size_t)pos * c.ngb_cap, c.h_ngb_list + (size_t)pos * c.ngb_cap + have);
+    }
+    std::sort(merged.begin(), merged.end());
+    const int ncopy = std::min((int)merged.size(), *maxlength);
+    if (ncopy > 0) memcpy(neighbour_list, merged.data(), sizeof(int) * ncopy);
+    *n_neighbours = (int)cnt;
+    // overflow when the list does not fit with room to spare: nblen >= maxlength (sapporo.cpp:262-265; ph4 shrinks
+    // h2 on it, gpu.cc:668-751)
+    return (cnt >= *maxlength || truncated) ? 1 : 0;
 }
 
 // ---- by-value variants (lib/g6lib/g6lib.h:58-128) ---------------------------
@@ -1126,26 +1590,41 @@ int g6_get_neighbour_list_sort_mode(void) { return g_sort_mode; }
 int g6_set_overflow_flag_test_mode(int aflag, int jflag, int pflag) { (void)aflag; (void)jflag; (void)pflag; return 0; }
 void force_j_particle_send(void)
 {
-    if (G.open) flush_updates();
+    for (int k = 0; k < M.n; k++) {
+        use(k);
+        flush_updates();
+    }
+    if (M.n > 0) use(0);
 }
 int get_j_part_data(int addr, int nj, double *pos, double *vel, double *acc, double *jrk, double *ppos, double *pvel)
 {
     require_open("get_j_part_data");
+    if (addr < 0 || addr >= nj) return -1;
+    use(owner_of(addr));
+    const int la = local_address(addr);
     flush_updates();
-    if (addr < 0 || addr >= nj || addr >= G.capacity) return -1;
+    if (la >= G.capacity) {
+        use(0);
+        return -1;
+    }
+    const int slot = G.h_slot_of[la];
     double2 q[7];
-    float4 abc[3];
+    float4 abc[4];
     CK(cudaStreamSynchronize(G.stream));
-    for (int k = 0; k < 7; k++) CK(cudaMemcpy(&q[k], G.js.q[k] + addr, sizeof(double2), cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(&abc[0], G.js.A + addr, sizeof(float4), cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(&abc[1], G.js.B + addr, sizeof(float4), cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(&abc[2], G.js.C + addr, sizeof(float4), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 7; k++) CK(cudaMemcpy(&q[k], G.js.q[k] + slot, sizeof(double2), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&abc[0], G.js.A + slot, sizeof(float4), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&abc[1], G.js.B + slot, sizeof(float4), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&abc[2], G.js.C + slot, sizeof(float4), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&abc[3], G.js.L + slot, sizeof(float4), cudaMemcpyDeviceToHost));
     if (pos) { pos[0] = q[0].x; pos[1] = q[0].y; pos[2] = q[1].x; }
     if (vel) { vel[0] = q[2].x; vel[1] = q[2].y; vel[2] = q[3].x; }
     if (acc) { acc[0] = q[3].y; acc[1] = q[4].x; acc[2] = q[4].y; }
     if (jrk) { jrk[0] = q[5].x; jrk[1] = q[5].y; jrk[2] = q[6].x; }
-    if (ppos) { ppos[0] = (double)abc[0].x + abc[1].x; ppos[1] = (double)abc[0].y + abc[1].y; ppos[2] = (double)abc[0].z + abc[1].z; }
-    if (pvel) { pvel[0] = abc[2].x; pvel[1] = abc[2].y; pvel[2] = abc[2].z; }
+    if (ppos)
+        for (int d = 0; d < 3; d++) ppos[d] = (double)(&abc[0].x)[d] + (double)(&abc[1].x)[d] + G.js.x0[d];
+    if (pvel)
+        for (int d = 0; d < 3; d++) pvel[d] = (double)(&abc[2].x)[d] + (double)(&abc[3].x)[d];
+    use(0);
     return 0;
 }
 
@@ -1166,9 +1645,24 @@ int g6x_set_stream(void *cuda_stream, int external)
 
 int g6x_set_refine(int on)
 {
-    G.refine = on ? 1 : 0;
+    for (int k = 0; k < std::max(1, M.n); k++) g_ctx[k].refine = on ? 1 : 0;
     return 0;
 }
+
+int g6x_set_close_factor(double k_close, double far_factor)
+{
+    for (int k = 0; k < std::max(1, M.n); k++) {
+        Context &c = g_ctx[k];
+        if (k_close >= 0.0) c.kclose = (float)k_close;
+        if (far_factor >= 0.0) c.farc = (float)far_factor;
+        c.ord.kclose = c.kclose;
+        c.ord.farc2 = c.farc * c.farc;
+    }
+    return 0;
+}
+
+long long g6x_order_rebuilds(void) { return g_ctx[0].order_rebuilds; }
+int g6x_device_count_open(void) { return M.n; }
 
 int g6x_set_j_offset(int offset)
 {
@@ -1183,6 +1677,20 @@ int g6x_set_j_particles(int n, const int *address, int address0, const int *inde
     require_open("g6x_set_j_particles");
     static const double zero3[3] = {0, 0, 0};
     if (n <= 0) return 0;
+    if (M.n > 1) {   // one j-memory over several devices: every particle goes to its owner
+        for (int k = 0; k < n; k++) {
+            const int a = address ? address[k] : address0 + k;
+            if (a < 0) {
+                fprintf(stderr, "g6_b200: FATAL g6x_set_j_particles address %d < 0\n", a);
+                exit(-1);
+            }
+            use(owner_of(a));
+            stage_j(local_address(a), index[k], tj ? tj[k] : 0.0, mass[k], j6 ? j6[k] : zero3, a2 ? a2[k] : zero3, v[k],
+                    x[k], a);
+        }
+        use(0);
+        return 0;
+    }
     int maxaddr = address0 + n - 1;
     if (address)
         for (int k = 0; k < n; k++) maxaddr = std::max(maxaddr, address[k]);
@@ -1197,9 +1705,15 @@ int g6x_set_j_particles(int n, const int *address, int address0, const int *inde
 int g6x_predict(int nj, double ti)
 {
     require_open("g6x_predict");
-    G.ti = ti;
-    flush_updates();
-    run_predictor(nj);
+    const int nd = std::max(1, M.n);
+    for (int k = 0; k < nd; k++) {
+        use(k);
+        G.ti = ti;
+        flush_updates();
+        if (order_stale(local_count(nj, k))) rebuild_order(local_count(nj, k));
+        run_predictor(local_count(nj, k));
+    }
+    use(0);
     return 0;
 }
 
@@ -1215,8 +1729,9 @@ static ExchangeSlots exchange_begin(int ni, const char *who)
                 P.attached ? "i-set exceeds the exchange capacity" : "no peers attached", ni, P.cap);
         exit(-1);
     }
-    P.seq++;
     ExchangeSlots e{};
+    if (ni <= 0) return e;   // nothing is exchanged (and no flag/combine kernel runs): the sequence must not advance
+    P.seq++;
     for (int r = 0; r < P.world; r++) e.half[r] = P.peer_buf[r] + (P.seq & 1) * P.half_bytes + P.rank * P.slot_bytes;
     return e;
 }
@@ -1264,9 +1779,116 @@ static void exchange_finish(int ni, double *d_sum, unsigned long long *d_key, in
     CK(cudaGetLastError());
     const int ctas = std::max(1, std::min(2 * G.sm_count, (ni + 255) / 256));
     peer_combine_kernel<<<ctas, 256, 0, G.stream>>>(ps, P.seq, ni, d_sum, reinterpret_cast<u64 *>(d_key), d_nnid,
-                                                    P.dev_h_err);
+                                                    P.dev_h_err, nullptr, 0ull);
     CK(cudaGetLastError());
     G.launches += 2;
+}
+
+// ---- in-process device group (multi-device ABI): peer access enabled directly, exchange buffers shared by
+// pointer, partials gathered at device 0 ------------------------------------------------------------
+static void peer_group_setup()
+{
+    const int n = M.n;
+    for (int k = 0; k < n; k++) {
+        use(k);
+        for (int r = 0; r < n; r++) {
+            if (r == k) continue;
+            int can = 0;
+            CK(cudaDeviceCanAccessPeer(&can, g_ctx[k].device, g_ctx[r].device));
+            if (!can) {
+                fprintf(stderr, "g6_b200: FATAL G6_B200_DEVICES=%d: device %d cannot access device %d's memory\n", n,
+                        g_ctx[k].device, g_ctx[r].device);
+                exit(-1);
+            }
+            cudaError_t e = cudaDeviceEnablePeerAccess(g_ctx[r].device, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) (void)cudaGetLastError();
+            else CK(e);
+        }
+        Context::Peer &P = G.peer;
+        P.world = n;
+        P.rank = k;
+        P.cap = (G.npipes + 15) / 16 * 16;
+        P.slot_bytes = (size_t)P.cap * (sizeof(double) * 7 + sizeof(u64) + sizeof(int));
+        P.half_bytes = P.slot_bytes * n;
+        P.flags_off = 2 * P.half_bytes;
+        P.buf_bytes = P.flags_off + 2 * sizeof(unsigned long long) * n;
+        CK(cudaMalloc((void **)&P.buf, P.buf_bytes));
+        CK(cudaMemset(P.buf, 0, P.buf_bytes));
+        host_alloc(P.h_err, 1);
+        P.h_err[0] = 0;
+        P.dev_h_err = dev_alias(P.h_err);
+        P.seq = 0;
+        P.allocated = true;
+        P.ipc = false;
+    }
+    for (int k = 0; k < n; k++) {
+        Context::Peer &P = g_ctx[k].peer;
+        for (int r = 0; r < n; r++) P.peer_buf[r] = g_ctx[r].peer.buf;
+        P.attached = true;
+    }
+    use(0);
+}
+
+// all devices: next exchange sequence number
+static void gather_begin_all(int ni)
+{
+    for (int k = 0; k < M.n; k++) {
+        Context::Peer &P = g_ctx[k].peer;
+        if (ni > P.cap) {
+            fprintf(stderr, "g6_b200: FATAL i-block of %d exceeds the exchange capacity %d\n", ni, P.cap);
+            exit(-1);
+        }
+        P.seq++;
+    }
+}
+// device k's force launch: its outputs go to slot k of the ROOT's exchange buffer (a local store for the root,
+// stores over NVLink for the others)
+static void gather_launch(int k, int nj, int ni, const IBlock &ib, float eps2, double *, u64 *, int *,
+                          const float4 *inline_src, unsigned long long)
+{
+    Context::Peer &P = G.peer;   // == g_ctx[k].peer (the caller selected device k)
+    unsigned char *slot = P.peer_buf[0] + (P.seq & 1) * P.half_bytes + (size_t)k * P.slot_bytes;
+    double *ssum = reinterpret_cast<double *>(slot);
+    u64 *skey = reinterpret_cast<u64 *>(slot + sizeof(double) * 7 * (size_t)P.cap);
+    int *sid = reinterpret_cast<int *>(slot + sizeof(double) * 8 * (size_t)P.cap);
+    G.mir_n = 0;
+    launch_force(nj, ni, ib, eps2, true, false, ssum, skey, sid, inline_src);
+    // tell the root this device's slot is complete
+    PeerSlots ps{};
+    ps.world = P.world;
+    ps.rank = k;
+    const size_t foff = P.flags_off + (P.seq & 1) * sizeof(unsigned long long) * P.world;
+    ps.flag = reinterpret_cast<volatile unsigned long long *>(P.peer_buf[0] + foff);   // the root's flags
+    ps.n_remote = 0;
+    peer_flag_kernel<<<1, 32, 0, G.stream>>>(ps, P.seq);
+    CK(cudaGetLastError());
+    G.launches++;
+}
+// root: wait for all flags, combine, write the totals to d_sum (or straight to mapped host memory + flag)
+static void gather_finish_all(int ni, bool direct)
+{
+    use(0);
+    Context::Peer &P = G.peer;
+    PeerSlots ps{};
+    ps.world = P.world;
+    ps.rank = 0;
+    unsigned char *mine = P.buf + (P.seq & 1) * P.half_bytes;
+    for (int r = 0; r < P.world; r++) {
+        unsigned char *b = mine + r * P.slot_bytes;
+        ps.sum[r] = reinterpret_cast<const double *>(b);
+        ps.key[r] = reinterpret_cast<const u64 *>(b + sizeof(double) * 7 * (size_t)P.cap);
+        ps.id[r] = reinterpret_cast<const int *>(b + sizeof(double) * 8 * (size_t)P.cap);
+    }
+    const size_t foff = P.flags_off + (P.seq & 1) * sizeof(unsigned long long) * P.world;
+    ps.flag = reinterpret_cast<volatile unsigned long long *>(P.buf + foff);
+    ps.n_remote = 0;
+    double *out = direct ? G.dev_h_sum : G.d_sum;
+    const int ctas = direct ? 1 : std::max(1, std::min(2 * G.sm_count, (ni + 255) / 256));
+    peer_combine_kernel<<<ctas, 256, 0, G.stream>>>(ps, P.seq, ni, out, reinterpret_cast<u64 *>(G.d_key),
+                                                    reinterpret_cast<int *>(out + 7 * (size_t)ni), P.dev_h_err,
+                                                    direct ? G.dev_h_flag : nullptr, G.flag_seq);
+    CK(cudaGetLastError());
+    G.launches++;
 }
 
 // Shared body of the device-resident entry points.  With peers attached and `exchange` set, every launch
@@ -1277,6 +1899,7 @@ static int calc_device_impl(int nj, int ni, const int *d_index, const double *d_
                             int *d_nnid, bool exchange)
 {
     flush_updates();
+    if (order_stale(nj)) rebuild_order(nj);
     run_predictor(nj);
     bool nn = (flags & 1) != 0, list = (flags & 2) != 0;
     if (list) {
@@ -1286,28 +1909,61 @@ static int calc_device_impl(int nj, int ni, const int *d_index, const double *d_
     Context::Peer &P = G.peer;
     ExchangeSlots ex{};
     if (exchange) ex = exchange_begin(ni, "g6x_calc_device_allreduce");
-    const int chunk = device_chunk(ni, std::min(nj, G.capacity));
+    const int njc = std::min(nj, G.capacity);
+    const int chunk = device_chunk(ni, njc);
     if (chunk > G.i2_cap) {
         CK(cudaStreamSynchronize(G.stream));
         dev_free(G.d_i2);
-        dev_alloc(G.d_i2, (size_t)3 * chunk);
+        dev_free(G.d_conf2);
+        dev_alloc(G.d_i2, (size_t)4 * chunk);
+        dev_alloc(G.d_conf2, (size_t)chunk);
         G.i2_cap = chunk;
+    }
+    // the speculative kernel wants Morton-sorted i-particles (64 neighbours per warp): sort the whole set once,
+    // pack every chunk through the permutation, and let the kernels write their outputs to the caller's index
+    const bool sorted = (ni > 1) && G.ord.nkeys > 0 && is_fast_variant(choose_variant(std::min(ni, chunk), njc));
+    if (sorted) {
+        if (ni > G.isort_cap) {
+            CK(cudaStreamSynchronize(G.stream));
+            dev_free(G.d_ikey); dev_free(G.d_ikey_tmp); dev_free(G.d_iperm); dev_free(G.d_iperm_tmp);
+            dev_alloc(G.d_ikey, (size_t)ni); dev_alloc(G.d_ikey_tmp, (size_t)ni);
+            dev_alloc(G.d_iperm, (size_t)ni); dev_alloc(G.d_iperm_tmp, (size_t)ni);
+            G.isort_cap = ni;
+        }
+        i_key_kernel<<<(ni + 255) / 256, 256, 0, G.stream>>>(ni, d_xi, G.js, G.ord, G.d_ikey_tmp, G.d_iperm_tmp);
+        CK(cudaGetLastError());
+        size_t need = 0;
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, need, G.d_ikey_tmp, G.d_ikey, G.d_iperm_tmp, G.d_iperm, ni, 0, 30,
+                                           G.stream));
+        if (need > G.sort_tmp_bytes) {
+            CK(cudaStreamSynchronize(G.stream));
+            if (G.d_sort_tmp) cudaFree(G.d_sort_tmp);
+            CK(cudaMalloc(&G.d_sort_tmp, need));
+            G.sort_tmp_bytes = need;
+        }
+        CK(cub::DeviceRadixSort::SortPairs(G.d_sort_tmp, need, G.d_ikey_tmp, G.d_ikey, G.d_iperm_tmp, G.d_iperm, ni, 0, 30,
+                                           G.stream));
+        G.launches += 2;
     }
     for (int i0 = 0; i0 < ni; i0 += chunk) {
         int n = std::min(chunk, ni - i0);
-        float4 *A = G.d_i2, *B = G.d_i2 + G.i2_cap, *C = G.d_i2 + 2 * (size_t)G.i2_cap;
-        pack_i_kernel<<<(n + 255) / 256, 256, 0, G.stream>>>(n, d_index + i0, d_xi + 3 * (size_t)i0,
-                                                              d_vi + 3 * (size_t)i0, d_h2 ? d_h2 + i0 : nullptr, A, B,
-                                                              C);
+        const IBlock ib = iblock_of(G.d_i2, G.i2_cap, G.d_conf2, sorted ? G.d_iperm + i0 : nullptr);
+        // sorted: packed particle k of this chunk is caller particle d_iperm[i0 + k] and its outputs go there;
+        // otherwise the chunk is the caller's [i0, i0 + n) and so are its outputs
+        const int ob = sorted ? 0 : i0;
+        pack_i_kernel<<<(n + 255) / 256, 256, 0, G.stream>>>(
+            n, ib.iperm, d_index + ob, d_xi + 3 * (size_t)ob, d_vi + 3 * (size_t)ob, d_h2 ? d_h2 + ob : nullptr,
+            G.js.x0[0], G.js.x0[1], G.js.x0[2], const_cast<float4 *>(ib.A), const_cast<float4 *>(ib.B),
+            const_cast<float4 *>(ib.C), const_cast<float4 *>(ib.D));
         G.launches++;
         CK(cudaGetLastError());
         if (!exchange) {
-            launch_force(nj, n, A, B, C, (float)eps2, nn, false, d_sum + 7 * (size_t)i0, d_key + i0, d_nnid + i0);
+            launch_force(nj, n, ib, (float)eps2, nn, false, d_sum + 7 * (size_t)ob, d_key + ob, d_nnid + ob);
             continue;
         }
-        exchange_set_mirrors(ex, i0);
+        exchange_set_mirrors(ex, ob);
         unsigned char *own = ex.half[P.rank];
-        launch_force(nj, n, A, B, C, (float)eps2, nn, false, slot_sum(own, i0), slot_key(own, i0), slot_id(own, i0));
+        launch_force(nj, n, ib, (float)eps2, nn, false, slot_sum(own, ob), slot_key(own, ob), slot_id(own, ob));
         G.mir_n = 0;
     }
     if (exchange && ni > 0) exchange_finish(ni, d_sum, d_key, d_nnid);
@@ -1352,6 +2008,7 @@ int g6x_peer_alloc(int world, int rank, int capacity, void *handle_out)
     P.seq = 0;
     P.allocated = true;
     P.attached = false;
+    P.ipc = true;
     cudaIpcMemHandle_t h;
     CK(cudaIpcGetMemHandle(&h, P.buf));
     memcpy(handle_out, &h, sizeof(h));
@@ -1383,7 +2040,7 @@ int g6x_peer_detach(void)
     if (!P.allocated) return 0;
     if (G.open) CK(cudaStreamSynchronize(G.stream));
     for (int r = 0; r < P.world; r++)
-        if (P.attached && r != P.rank && P.peer_buf[r]) cudaIpcCloseMemHandle(P.peer_buf[r]);
+        if (P.attached && P.ipc && r != P.rank && P.peer_buf[r]) cudaIpcCloseMemHandle(P.peer_buf[r]);
     if (P.buf) cudaFree(P.buf);
     host_free(P.h_err);
     P = Context::Peer{};
@@ -1406,7 +2063,7 @@ int g6x_resolve_nn(int ni, const unsigned long long *d_key, int rank, int *d_nni
     require_open("g6x_resolve_nn");
     if (ni <= 0) return 0;
     resolve_nn_kernel<<<(ni + 255) / 256, 256, 0, G.stream>>>(ni, d_key, rank, G.j_offset,
-                                                               std::min(G.nj_hi, G.capacity), G.js.B, d_nnid);
+                                                               std::min(G.nj_hi, G.capacity), G.js.slot_of, G.js.B, d_nnid);
     G.launches++;
     CK(cudaGetLastError());
     return 0;
@@ -1421,7 +2078,8 @@ static void hermite_reserve(int n)
     int cap = std::max(n, std::max(4096, 2 * H.cap));
     host_free(H.h_ilist); host_free(H.h_olddt); host_free(H.h_outdt); host_free(H.h_outpot); host_free(H.h_outnn);
     dev_free(H.d_pred); dev_free(H.d_i); dev_free(H.d_sum); dev_free(H.d_key); dev_free(H.d_nnid);
-    dev_free(H.d_ilist); dev_free(H.d_olddt);
+    dev_free(H.d_ilist); dev_free(H.d_olddt); dev_free(H.d_conf);
+    dev_alloc(H.d_conf, (size_t)cap);
     dev_alloc(H.d_ilist, (size_t)cap);
     dev_alloc(H.d_olddt, (size_t)cap);
     host_alloc(H.h_ilist, cap);   H.dev_h_ilist = dev_alias(H.h_ilist);
@@ -1430,7 +2088,7 @@ static void hermite_reserve(int n)
     host_alloc(H.h_outpot, cap);  H.dev_h_outpot = dev_alias(H.h_outpot);
     host_alloc(H.h_outnn, cap);   H.dev_h_outnn = dev_alias(H.h_outnn);
     dev_alloc(H.d_pred, (size_t)6 * cap);
-    dev_alloc(H.d_i, (size_t)3 * cap);
+    dev_alloc(H.d_i, (size_t)4 * cap);
     dev_alloc(H.d_sum, (size_t)7 * cap);
     dev_alloc(H.d_key, (size_t)cap);
     dev_alloc(H.d_nnid, (size_t)cap);
@@ -1451,7 +2109,9 @@ static void hermite_pass(int nj, int n, double tnext, double eta, double eps2, i
     h.tnext = tnext;
     h.eta = eta;
     h.js = G.js;
-    h.iA = H.d_i; h.iB = H.d_i + n; h.iC = H.d_i + 2 * (size_t)n;
+    h.slot_of = G.js.slot_of;
+    h.iA = H.d_i; h.iB = H.d_i + n; h.iC = H.d_i + 2 * (size_t)n; h.iD = H.d_i + 3 * (size_t)n;
+    const IBlock ib = iblock_of(H.d_i, n, H.d_conf);
     h.pred = H.d_pred;
     h.sum = H.d_sum;
     h.nnid = H.d_nnid;
@@ -1463,32 +2123,29 @@ static void hermite_pass(int nj, int n, double tnext, double eta, double eps2, i
     const int ctas = (n + 255) / 256;
     G.ti = tnext;
     if (H.shard_hi > 0) {
-        // replicated state, sharded forces: gather the block (every rank, identical), predict only this
-        // rank's j-window, sum over it with the partials mirrored into the peers' exchange buffers, combine,
-        // and let every rank correct its own replica with the identical totals
+        // replicated state, sharded forces: gather the block (every rank, identical), predict (every rank, all j:
+        // the neighbour bounds of the speculative kernel look at the whole j-memory), sum over this rank's window
+        // of the SLOTS with the partials mirrored into the peers' exchange buffers, combine, and let every rank
+        // correct its own replica with the identical totals.  The Morton permutation is a function of the state,
+        // which is identical on all ranks, so a window of slots holds the same particles everywhere.
         int lo = H.shard_lo, hi = std::min(H.shard_hi, std::min(nj, G.capacity));
         if (hi <= lo) lo = hi = 0;   // empty window (more ranks than j-tiles): this rank contributes zeros
         hermite_gather_kernel<<<ctas, 256, 0, G.stream>>>(h);
         CK(cudaGetLastError());
-        if (hi > lo) {
-            const int tile0 = lo / TILE, ntiles = (hi - lo + TILE - 1) / TILE;
-            const int npred = std::max(std::min(nj, G.capacity), std::min(G.nj_hi, G.capacity));
-            predict_kernel<<<ntiles, TILE, 0, G.stream>>>(std::min(npred, hi), tnext, G.js, tile0);
-            CK(cudaGetLastError());
-        }
+        G.j_dirty = true;
+        run_predictor(nj);
         ExchangeSlots ex = exchange_begin(n, "g6x_hermite_step (sharded)");
         exchange_set_mirrors(ex, 0);
         unsigned char *own = ex.half[G.peer.rank];
         G.win_lo = lo;
-        launch_force(std::max(0, hi - lo), n, h.iA, h.iB, h.iC, (float)eps2, true, false, slot_sum(own, 0),
-                     slot_key(own, 0), slot_id(own, 0));
+        launch_force(std::max(0, hi - lo), n, ib, (float)eps2, true, false, slot_sum(own, 0), slot_key(own, 0),
+                     slot_id(own, 0));
         G.win_lo = 0;
         G.mir_n = 0;
         exchange_finish(n, H.d_sum, reinterpret_cast<unsigned long long *>(H.d_key), H.d_nnid);
         hermite_correct_kernel<<<ctas, 256, 0, G.stream>>>(h);
         CK(cudaGetLastError());
         G.launches += 3;
-        G.predicted_nj = -1;   // only a window was predicted
     } else if (n <= 384 && G.variant == V_AUTO) {
         // small block: two launches -- (predict all j + gather/predict the block), then the force kernel
         // whose final-output stage is the corrector
@@ -1500,14 +2157,13 @@ static void hermite_pass(int nj, int n, double tnext, double eta, double eps2, i
         G.predicted_nj = npred;
         G.predicted_ti = tnext;
         G.j_dirty = false;
-        launch_force(nj, n, h.iA, h.iB, h.iC, (float)eps2, true, false, H.d_sum, H.d_key, H.d_nnid, nullptr,
-                     h.flag_seq, &h);
+        launch_force(nj, n, ib, (float)eps2, true, false, H.d_sum, H.d_key, H.d_nnid, nullptr, h.flag_seq, &h);
         G.launches += 1;
     } else {
         hermite_gather_kernel<<<ctas, 256, 0, G.stream>>>(h);
         CK(cudaGetLastError());
         run_predictor(nj);
-        launch_force(nj, n, h.iA, h.iB, h.iC, (float)eps2, true, false, H.d_sum, H.d_key, H.d_nnid);
+        launch_force(nj, n, ib, (float)eps2, true, false, H.d_sum, H.d_key, H.d_nnid);
         hermite_correct_kernel<<<ctas, 256, 0, G.stream>>>(h);
         CK(cudaGetLastError());
         G.launches += 2;
@@ -1524,15 +2180,35 @@ int g6x_hermite_step(int nj, int ni, const int *ilist, double tnext, double eta,
     if (G.pending) CK(cudaStreamSynchronize(G.stream));
     flush_updates();
     if (ni <= 0) return 0;
+    G.updates_since_order += ni;   // the corrector moves particles without passing through stage_j
+    if (order_stale(nj)) rebuild_order(nj);
     // the whole block in one pass, whatever its size: every force is computed against the PREDICTED state
     // of all j before any particle is corrected, as in idata::advance
     hermite_reserve(ni);
-    memcpy(H.h_ilist, ilist, sizeof(int) * ni);
-    memcpy(H.h_olddt, old_dt, sizeof(double) * ni);
+    // big blocks go to the speculative kernel, which wants Morton neighbours side by side: the slots ARE in
+    // Morton order, so the block is walked in slot order
+    const bool sorted = ni > 384;
+    static std::vector<int> order;
+    if (sorted) {
+        order.resize(ni);
+        for (int k = 0; k < ni; k++) order[k] = k;
+        const int *so = G.h_slot_of.data();
+        std::sort(order.begin(), order.end(), [&](int a, int b) { return so[ilist[a]] < so[ilist[b]]; });
+        for (int k = 0; k < ni; k++) {
+            H.h_ilist[k] = ilist[order[k]];
+            H.h_olddt[k] = old_dt[order[k]];
+        }
+    } else {
+        memcpy(H.h_ilist, ilist, sizeof(int) * ni);
+        memcpy(H.h_olddt, old_dt, sizeof(double) * ni);
+    }
     hermite_pass(nj, ni, tnext, eta, eps2, 0);
-    memcpy(new_dt, H.h_outdt, sizeof(double) * ni);
-    if (pot) memcpy(pot, H.h_outpot, sizeof(double) * ni);
-    if (nn) memcpy(nn, H.h_outnn, sizeof(int) * ni);
+    for (int k = 0; k < ni; k++) {
+        const int i = sorted ? order[k] : k;
+        new_dt[i] = H.h_outdt[k];
+        if (pot) pot[i] = H.h_outpot[k];
+        if (nn) nn[i] = H.h_outnn[k];
+    }
     return 0;
 }
 
@@ -1556,12 +2232,17 @@ int g6x_hermite_init(int nj, double t0, double eta, double eps2, double *timeste
     flush_updates();
     nj = std::min(nj, G.capacity);
     if (nj <= 0) return -1;
+    if (order_stale(nj)) rebuild_order(nj);
     hermite_reserve(nj);
     H.time.assign(nj, t0);
     H.dt.assign(nj, 0.0);
-    for (int k = 0; k < nj; k++) H.h_ilist[k] = k;
+    {   // all particles, walked in slot (= Morton) order
+        std::vector<int> addr_of_slot(nj, 0);
+        for (int a = 0; a < nj; a++) addr_of_slot[G.h_slot_of[a]] = a;
+        for (int k = 0; k < nj; k++) H.h_ilist[k] = addr_of_slot[k];
+    }
     hermite_pass(nj, nj, t0, eta, eps2, 1);   // forces of all particles at t0, first steps (jdata.cc:503-548)
-    memcpy(H.dt.data(), H.h_outdt, sizeof(double) * nj);
+    for (int k = 0; k < nj; k++) H.dt[H.h_ilist[k]] = H.h_outdt[k];
     if (timestep_out) memcpy(timestep_out, H.dt.data(), sizeof(double) * nj);
     H.system_time = t0;
     H.block_steps = H.particle_steps = 0;
@@ -1636,12 +2317,13 @@ int g6x_hermite_get_state(int nj, double *t, double (*x)[3], double (*v)[3], dou
         q[k].resize(nj);
         CK(cudaMemcpy(q[k].data(), G.js.q[k], sizeof(double2) * nj, cudaMemcpyDeviceToHost));
     }
-    for (int i = 0; i < nj; i++) {
-        if (x) { x[i][0] = q[0][i].x; x[i][1] = q[0][i].y; x[i][2] = q[1][i].x; }
-        if (t) t[i] = q[1][i].y;
-        if (v) { v[i][0] = q[2][i].x; v[i][1] = q[2][i].y; v[i][2] = q[3][i].x; }
-        if (a) { a[i][0] = q[3][i].y; a[i][1] = q[4][i].x; a[i][2] = q[4][i].y; }
-        if (j) { j[i][0] = q[5][i].x; j[i][1] = q[5][i].y; j[i][2] = q[6][i].x; }
+    for (int i = 0; i < nj; i++) {   // caller's address i lives in slot s (addresses [0, nj) occupy slots [0, nj))
+        const int s = G.h_slot_of[i] < nj ? G.h_slot_of[i] : i;
+        if (x) { x[i][0] = q[0][s].x; x[i][1] = q[0][s].y; x[i][2] = q[1][s].x; }
+        if (t) t[i] = q[1][s].y;
+        if (v) { v[i][0] = q[2][s].x; v[i][1] = q[2][s].y; v[i][2] = q[3][s].x; }
+        if (a) { a[i][0] = q[3][s].y; a[i][1] = q[4][s].x; a[i][2] = q[4][s].y; }
+        if (j) { j[i][0] = q[5][s].x; j[i][1] = q[5][s].y; j[i][2] = q[6][s].x; }
     }
     return 0;
 }
@@ -1667,16 +2349,21 @@ int g6x_read_predicted(int nj, double (*pos)[3], double (*vel)[3])
 {
     require_open("g6x_read_predicted");
     nj = std::min(nj, G.capacity);
-    std::vector<float4> A(nj), B(nj), C(nj);
+    const int n = std::min(G.capacity, std::max(nj, G.nj_hi));   // slots that may hold addresses < nj
+    std::vector<float4> A(n), B(n), C(n), L(n);
     CK(cudaStreamSynchronize(G.stream));
-    CK(cudaMemcpy(A.data(), G.js.A, sizeof(float4) * nj, cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(B.data(), G.js.B, sizeof(float4) * nj, cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(C.data(), G.js.C, sizeof(float4) * nj, cudaMemcpyDeviceToHost));
-    for (int j = 0; j < nj; j++) {
-        pos[j][0] = (double)A[j].x + (double)B[j].x;
-        pos[j][1] = (double)A[j].y + (double)B[j].y;
-        pos[j][2] = (double)A[j].z + (double)B[j].z;
-        vel[j][0] = C[j].x; vel[j][1] = C[j].y; vel[j][2] = C[j].z;
+    CK(cudaMemcpy(A.data(), G.js.A, sizeof(float4) * n, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(B.data(), G.js.B, sizeof(float4) * n, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(C.data(), G.js.C, sizeof(float4) * n, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(L.data(), G.js.L, sizeof(float4) * n, cudaMemcpyDeviceToHost));
+    for (int j = 0; j < nj; j++) {   // by the caller's address; positions back in the caller's frame
+        const int s = G.h_slot_of[j];
+        pos[j][0] = (double)A[s].x + (double)B[s].x + G.js.x0[0];
+        pos[j][1] = (double)A[s].y + (double)B[s].y + G.js.x0[1];
+        pos[j][2] = (double)A[s].z + (double)B[s].z + G.js.x0[2];
+        vel[j][0] = (double)C[s].x + (double)L[s].x;
+        vel[j][1] = (double)C[s].y + (double)L[s].y;
+        vel[j][2] = (double)C[s].z + (double)L[s].z;
     }
     return 0;
 }
@@ -1724,7 +2411,7 @@ double g6x_latency_probe(int kernels, int reps)
 int g6x_set_variant(int variant)
 {
     if (variant < 0 || variant >= V_COUNT) return -1;
-    G.variant = variant;
+    for (int k = 0; k < std::max(1, M.n); k++) g_ctx[k].variant = variant;
     return 0;
 }
 

@@ -4,8 +4,11 @@
 //   scatter_kernel          j-update scatter                              (HBM/latency-bound)
 //   update_predict_kernel   scatter of a small update batch + predictor in one launch
 //   pack_i_kernel           double -> double-single i-block packing (device callers)
-//   force_fast_kernel<>     Hermite force, big i-blocks: acc, jerk, pot, nearest neighbour; mask-free groups of
-//                           pairs verified afterwards (speculative)       (FP32-pipe-bound)
+//   force_fast_kernel<>     Hermite force, big i-blocks: acc, jerk, pot, nearest neighbour; (warp of i) x (group of j)
+//                           blocks classified by bounding boxes into FAR (hi-part differences), NEAR (mask-free
+//                           double-single) and CLOSE (FP64, the reference's rule)       (FP32-pipe-bound)
+//   near_kernel             its pre-pass: id-table lookup + nearest-neighbour bound per i-particle
+//   order_*_kernel, hash_insert_kernel, i_key_kernel   Morton order of the j-memory, id -> slot table
 //   force_kernel<>          Hermite force, small i-blocks and neighbour-sphere lists: j split over the warps of a
 //                           CTA, masks per pair; optional i-block in the kernel parameters, results and completion
 //                           flag in mapped host memory, corrector in the output stage   (latency-bound)
@@ -32,6 +35,8 @@ namespace g6b {
 constexpr int THREADS = 256;   // threads per force CTA (8 warps)
 constexpr int TILE = 256;      // j-particles per shared-memory stage
 constexpr int STAGES = 3;      // TMA bulk-copy pipeline depth
+constexpr int GROUPS_PER_TILE = TILE / 32;
+constexpr int TBOX = 2 * GROUPS_PER_TILE + 2;   // float4 per tile in gbb: 8 group boxes + the tile's own box
 #ifndef G6_FLUSH
 #define G6_FLUSH 16
 #endif
@@ -45,16 +50,28 @@ constexpr float FAR_AWAY = 1.0e18f;  // where massless / unused j are parked
 constexpr unsigned long long KEY_NONE = 0x7f800000ffffffffULL;
 
 // ---------------------------------------------------------------------------
-// j state in HBM (capacity C, padded to a multiple of TILE), all FP64 like the
-// reference's jdata arrays, packed as seven double2 streams (7 x LDG.128 per j):
+// j state in HBM (capacity C, padded to a multiple of TILE), indexed by SLOT.  The library keeps
+// the j-memory in Morton order of the positions (rebuilt after bulk loads, see "j-memory order"
+// below); the caller's addresses are translated through slot_of[] when updates arrive.  All FP64
+// like the reference's jdata arrays, packed as seven double2 streams (7 x LDG.128 per j):
 //   q0 = (x, y)    q1 = (z, t_j)   q2 = (vx, vy)   q3 = (vz, ax)
-//   q4 = (ay, az)  q5 = (jx, jy)   q6 = (jz, {float mass, int id})
-// predicted j (what the force kernel streams), float4 each:
-//   A = (x.hi, y.hi, z.hi, mass)  B = (x.lo, y.lo, z.lo, id bits)  C = (vx, vy, vz, 0)
+//   q4 = (ay, az)  q5 = (jx, jy)   q6 = (jz, mass)
+//   ia = (id, address reported in nearest-neighbour keys)
+// predicted j (what the force kernels stream), float4 each, positions relative to the origin x0:
+//   A = (x.hi, y.hi, z.hi, mass)  B = (x.lo, y.lo, z.lo, id bits)  C = (vx, vy, vz, address bits)
+//   L = (vx.lo, vy.lo, vz.lo, mass.lo)   -- read by the FP64 pairs only
+// and per tile TBOX float4 of bounding boxes of the hi parts of the massive members, (min x, min y,
+// min z, largest |coordinate|), (max x, max y, max z, 0): eight group boxes (32 slots each), then the tile's.
 // ---------------------------------------------------------------------------
 struct JState {
     double2 *q[7];
-    float4 *A, *B, *C;
+    int2 *ia;
+    float4 *A, *B, *C, *L;
+    float4 *gbb;
+    int *slot_of;        // [address] -> slot
+    float *near2;        // [slot] squared distance to the nearest neighbour when the particle was last an
+                         // i-particle (or an upper bound from the Morton window at the last re-ordering)
+    double x0[3];        // origin subtracted from every position before the hi/lo split
 };
 
 // One staged j-update (host pinned -> device staging -> scatter_kernel).
@@ -64,28 +81,25 @@ struct __align__(16) JUpdate {
     double a[3];
     double j[3];
     double t;
-    float m;
+    double m;
     int id;
-    int addr;
-    int pad[3];
+    int slot;      // where it goes (the host keeps a mirror of slot_of[])
+    int kaddr;     // address reported in nearest-neighbour keys
+    int addr;      // the caller's (local) address
 };
 static_assert(sizeof(JUpdate) == 128, "JUpdate layout");
 
-__device__ __forceinline__ double pack_mass_id(float m, int id)
-{
-    return __hiloint2double(id, __float_as_int(m));
-}
-
 __device__ __forceinline__ void store_update(const JUpdate &u, const JState &s)
 {
-    const int a = u.addr;
+    const int a = u.slot;
     s.q[0][a] = make_double2(u.x[0], u.x[1]);
     s.q[1][a] = make_double2(u.x[2], u.t);
     s.q[2][a] = make_double2(u.v[0], u.v[1]);
     s.q[3][a] = make_double2(u.v[2], u.a[0]);
     s.q[4][a] = make_double2(u.a[1], u.a[2]);
     s.q[5][a] = make_double2(u.j[0], u.j[1]);
-    s.q[6][a] = make_double2(u.j[2], pack_mass_id(u.m, u.id));
+    s.q[6][a] = make_double2(u.j[2], u.m);
+    s.ia[a] = make_int2(u.id, u.kaddr);
 }
 __global__ void scatter_kernel(int n, const JUpdate *__restrict__ up, JState s)
 {
@@ -94,78 +108,121 @@ __global__ void scatter_kernel(int n, const JUpdate *__restrict__ up, JState s)
     store_update(up[k], s);
 }
 
-// Hermite predictor (jdata.cc:726-747) in FP64, output split to double-single.
-// Algorithmic traffic: 112 B read + 48 B written per j.
-// One CTA = one j-tile (TILE = 256 slots; the arrays are padded to whole tiles).  The CTA also
-// records the id range of its massive particles in the spare .w lanes of the tile's first two C
-// entries (C[tile*256].w = min id, C[tile*256+1].w = max id, as int bits): the force kernel uses
-// it to decide per tile whether the self-exclusion masks can be skipped.
-// predict_tile: the body, for one tile and the 256 threads of a CTA.  sh_lo/sh_hi: TILE/32 ints of
-// shared memory each.
-__device__ __forceinline__ void predict_tile(const int tile, const int n, const double ti, const JState &s, int *sh_lo,
-                                             int *sh_hi)
+// identity order / no neighbour bound for freshly allocated slots [lo, hi)
+__global__ void order_fill_kernel(const int lo, const int hi, int *slot_of, int *addr_of, float *near2)
 {
-    const int j = tile * TILE + threadIdx.x;   // always < capacity
+    const int j = lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= hi) return;
+    slot_of[j] = j;
+    addr_of[j] = j;
+    near2[j] = __int_as_float(0x7f800000);
+}
+
+// floats <-> integers with the same ordering (for min/max reductions with integer instructions)
+__device__ __forceinline__ int f2ord(float f)
+{
+    const int i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+// FP64 Hermite prediction of slot j to time ti (jdata.cc:726-747), same expression tree.
+struct PredJ {
+    double x, y, z, vx, vy, vz, m;
+};
+__device__ __forceinline__ PredJ predict_slot(const JState &s, const int j, const double ti)
+{
     const double2 q0 = s.q[0][j], q1 = s.q[1][j], q2 = s.q[2][j], q3 = s.q[3][j], q4 = s.q[4][j], q5 = s.q[5][j],
                   q6 = s.q[6][j];
     const double x = q0.x, y = q0.y, z = q1.x, tj = q1.y, vx = q2.x, vy = q2.y, vz = q3.x;
     const double ax = q3.y, ay = q4.x, az = q4.y, jx = q5.x, jy = q5.y, jz = q6.x;
-    const float m = __int_as_float(__double2loint(q6.y));
-    const int id = __double2hiint(q6.y);
     const double dt = ti - tj;
-    double px = x, py = y, pz = z, qx = vx, qy = vy, qz = vz;
+    PredJ p{x, y, z, vx, vy, vz, q6.y};
     if (dt != 0.0) {  // same expression tree as jdata.cc:739-746
-        px = x + dt * (vx + 0.5 * dt * (ax + dt * jx / 3));
-        py = y + dt * (vy + 0.5 * dt * (ay + dt * jy / 3));
-        pz = z + dt * (vz + 0.5 * dt * (az + dt * jz / 3));
-        qx = vx + dt * (ax + 0.5 * dt * jx);
-        qy = vy + dt * (ay + 0.5 * dt * jy);
-        qz = vz + dt * (az + 0.5 * dt * jz);
+        p.x = x + dt * (vx + 0.5 * dt * (ax + dt * jx / 3));
+        p.y = y + dt * (vy + 0.5 * dt * (ay + dt * jy / 3));
+        p.z = z + dt * (vz + 0.5 * dt * (az + dt * jz / 3));
+        p.vx = vx + dt * (ax + 0.5 * dt * jx);
+        p.vy = vy + dt * (ay + 0.5 * dt * jy);
+        p.vz = vz + dt * (az + 0.5 * dt * jz);
     }
-    const bool massive = (j < n) && (m > TINYF);
+    return p;
+}
+
+// Hermite predictor (jdata.cc:726-747) in FP64, output split to double-single.
+// Algorithmic traffic: 120 B read (seven double2 + id/address) + 65 B written per j.
+// One CTA = one j-tile (TILE = 256 slots; the arrays are padded to whole tiles), one warp = one
+// group of 32 slots, whose bounding box it records for the force kernel's far/close decisions.
+// sh: 7 x 8 ints of shared memory.
+__device__ __forceinline__ void predict_tile(const int tile, const int n, const double ti, const JState &s)
+{
+    __shared__ int sh[7][TILE / 32];
+    const int j = tile * TILE + threadIdx.x;   // always < capacity
+    PredJ p = predict_slot(s, j, ti);
+    const int2 ia = s.ia[j];
+    const bool massive = (j < n) && (p.m > (double)TINYF);
+    double px = p.x - s.x0[0], py = p.y - s.x0[1], pz = p.z - s.x0[2];
     if (!massive) {  // massless or never-set slot: park it (idata.cc:208)
         px = py = pz = (double)FAR_AWAY;
-        qx = qy = qz = 0.0;
+        p.vx = p.vy = p.vz = 0.0;
+        p.m = 0.0;
     }
-    int lo = __reduce_min_sync(0xffffffffu, massive ? id : 0x7fffffff);
-    int hi = __reduce_max_sync(0xffffffffu, massive ? id : (int)0x80000000);
+    // slots in [n, end of tile) are written too (parked): the force kernel bounds its j loop by nj anyway
+    const float xh = (float)px, yh = (float)py, zh = (float)pz;
+    const float xl = (float)(px - (double)xh), yl = (float)(py - (double)yh), zl = (float)(pz - (double)zh);
+    const float vxh = (float)p.vx, vyh = (float)p.vy, vzh = (float)p.vz, mh = (float)p.m;
+    s.A[j] = make_float4(xh, yh, zh, mh);
+    s.B[j] = make_float4(xl, yl, zl, __int_as_float(ia.x));
+    s.C[j] = make_float4(vxh, vyh, vzh, __int_as_float(ia.y));
+    s.L[j] = make_float4((float)(p.vx - (double)vxh), (float)(p.vy - (double)vyh), (float)(p.vz - (double)vzh),
+                         (float)(p.m - (double)mh));
+    // bounding box of the group's massive members (empty group: an inverted box nothing is close to)
+    const int big = 0x7f7fffff, small = f2ord(-3.0e38f);   // +-FLT_MAX-ish
+    const int lx = __reduce_min_sync(0xffffffffu, massive ? f2ord(xh) : big);
+    const int ly = __reduce_min_sync(0xffffffffu, massive ? f2ord(yh) : big);
+    const int lz = __reduce_min_sync(0xffffffffu, massive ? f2ord(zh) : big);
+    const int hx = __reduce_max_sync(0xffffffffu, massive ? f2ord(xh) : small);
+    const int hy = __reduce_max_sync(0xffffffffu, massive ? f2ord(yh) : small);
+    const int hz = __reduce_max_sync(0xffffffffu, massive ? f2ord(zh) : small);
+    const float amax = massive ? fmaxf(fmaxf(fabsf(xh), fabsf(yh)), fabsf(zh)) : 0.f;
+    const int sc = __reduce_max_sync(0xffffffffu, __float_as_int(amax));   // non-negative floats order like ints
+    const int w = threadIdx.x >> 5;
+    float4 *tb = s.gbb + (size_t)tile * TBOX;
     if ((threadIdx.x & 31) == 0) {
-        sh_lo[threadIdx.x >> 5] = lo;
-        sh_hi[threadIdx.x >> 5] = hi;
+        tb[2 * w] = make_float4(ord2f(lx), ord2f(ly), ord2f(lz), __int_as_float(sc));
+        tb[2 * w + 1] = make_float4(ord2f(hx), ord2f(hy), ord2f(hz), 0.f);
+        sh[0][w] = lx; sh[1][w] = ly; sh[2][w] = lz; sh[3][w] = hx; sh[4][w] = hy; sh[5][w] = hz; sh[6][w] = sc;
     }
     __syncthreads();
-    float cw = 0.f;
-    if (threadIdx.x < 2) {
+    if (threadIdx.x == 0) {
+        int r[7];
 #pragma unroll
-        for (int w = 0; w < TILE / 32; w++) {
-            lo = min(lo, sh_lo[w]);
-            hi = max(hi, sh_hi[w]);
+        for (int q = 0; q < 7; q++) r[q] = sh[q][0];
+#pragma unroll
+        for (int g = 1; g < TILE / 32; g++) {
+#pragma unroll
+            for (int q = 0; q < 3; q++) r[q] = min(r[q], sh[q][g]);
+#pragma unroll
+            for (int q = 3; q < 7; q++) r[q] = max(r[q], sh[q][g]);
         }
-        cw = __int_as_float(threadIdx.x == 0 ? lo : hi);
+        tb[2 * GROUPS_PER_TILE] = make_float4(ord2f(r[0]), ord2f(r[1]), ord2f(r[2]), __int_as_float(r[6]));
+        tb[2 * GROUPS_PER_TILE + 1] = make_float4(ord2f(r[3]), ord2f(r[4]), ord2f(r[5]), 0.f);
     }
-    // slots in [n, end of tile) are written too (parked): the tile's id range lives in its first two
-    // entries and the force kernel bounds its j loop by nj anyway
-    float xh = (float)px, yh = (float)py, zh = (float)pz;
-    float xl = (float)(px - (double)xh), yl = (float)(py - (double)yh), zl = (float)(pz - (double)zh);
-    s.A[j] = make_float4(xh, yh, zh, massive ? m : 0.f);
-    s.B[j] = make_float4(xl, yl, zl, __int_as_float(id));
-    s.C[j] = make_float4((float)qx, (float)qy, (float)qz, cw);
-    __syncthreads();   // sh_lo/sh_hi may be reused by the next tile
 }
 
 // Pending j-updates applied by the kernel that predicts (small batches, block-timestep regime): the
-// addresses ride in the kernel parameters, the 128-byte records are read from mapped pinned host
-// memory by the threads whose address falls into the CTA's j range [j_lo, j_hi).
+// slots ride in the kernel parameters, the 128-byte records are read from mapped pinned host
+// memory by the threads whose slot falls into the CTA's j range [j_lo, j_hi).
 constexpr int UPD_MAX = 256;
 struct InlineU {
     int n;
-    int addr[UPD_MAX];
+    int slot[UPD_MAX];
 };
 __device__ __forceinline__ void apply_updates(const InlineU &iu, const JUpdate *__restrict__ rec, const JState &s,
                                               const int j_lo, const int j_hi)
 {
     for (int k = threadIdx.x; k < iu.n; k += blockDim.x) {
-        const int a = iu.addr[k];
+        const int a = iu.slot[k];
         if (a >= j_lo && a < j_hi) store_update(rec[k], s);
     }
     __syncthreads();   // the block's own global writes are visible to its threads after the barrier
@@ -173,33 +230,38 @@ __device__ __forceinline__ void apply_updates(const InlineU &iu, const JUpdate *
 
 __global__ void __launch_bounds__(TILE) predict_kernel(int n, double ti, JState s, int tile0 = 0)
 {
-    __shared__ int sh_lo[TILE / 32], sh_hi[TILE / 32];
-    predict_tile(tile0 + blockIdx.x, n, ti, s, sh_lo, sh_hi);
+    predict_tile(tile0 + blockIdx.x, n, ti, s);
 }
 
 // scatter + predict in one launch (small update batches).
 __global__ void __launch_bounds__(TILE) update_predict_kernel(int n, double ti, JState s, const JUpdate *rec,
                                                               const __grid_constant__ InlineU iu)
 {
-    __shared__ int sh_lo[TILE / 32], sh_hi[TILE / 32];
     apply_updates(iu, rec, s, blockIdx.x * TILE, (blockIdx.x + 1) * TILE);
-    predict_tile(blockIdx.x, n, ti, s, sh_lo, sh_hi);
+    predict_tile(blockIdx.x, n, ti, s);
 }
 
-// i-block packing for device-resident callers: double -> double-single.
-//   iA = (x.hi,y.hi,z.hi,h2)  iB = (x.lo,y.lo,z.lo,id bits)  iC = (vx,vy,vz,0)
-__global__ void pack_i_kernel(int ni, const int *__restrict__ index, const double *__restrict__ xi,
-                              const double *__restrict__ vi, const double *__restrict__ h2,
-                              float4 *iA, float4 *iB, float4 *iC)
+// i-block packing for device-resident callers: double -> double-single, relative to the origin.
+//   iA = (x.hi,y.hi,z.hi,h2)  iB = (x.lo,y.lo,z.lo,id bits)  iC = (vx,vy,vz,0)  iD = (vx.lo,vy.lo,vz.lo,d2)
+// d2 (squared distance to a neighbour: an upper bound of the nearest-neighbour distance) is filled
+// in by near_kernel.  perm != NULL: packed slot k holds caller particle perm[k] (Morton order).
+__global__ void pack_i_kernel(int ni, const int *__restrict__ perm, const int *__restrict__ index,
+                              const double *__restrict__ xi, const double *__restrict__ vi,
+                              const double *__restrict__ h2, const double x0, const double y0, const double z0,
+                              float4 *iA, float4 *iB, float4 *iC, float4 *iD)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= ni) return;
-    double x = xi[3 * i], y = xi[3 * i + 1], z = xi[3 * i + 2];
-    float xh = (float)x, yh = (float)y, zh = (float)z;
-    iA[i] = make_float4(xh, yh, zh, h2 ? (float)h2[i] : 0.f);
-    iB[i] = make_float4((float)(x - (double)xh), (float)(y - (double)yh), (float)(z - (double)zh),
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= ni) return;
+    const int i = perm ? perm[k] : k;
+    const double x = xi[3 * (size_t)i] - x0, y = xi[3 * (size_t)i + 1] - y0, z = xi[3 * (size_t)i + 2] - z0;
+    const double vx = vi[3 * (size_t)i], vy = vi[3 * (size_t)i + 1], vz = vi[3 * (size_t)i + 2];
+    const float xh = (float)x, yh = (float)y, zh = (float)z;
+    const float vxh = (float)vx, vyh = (float)vy, vzh = (float)vz;
+    iA[k] = make_float4(xh, yh, zh, h2 ? (float)h2[i] : 0.f);
+    iB[k] = make_float4((float)(x - (double)xh), (float)(y - (double)yh), (float)(z - (double)zh),
                         __int_as_float(index[i]));
-    iC[i] = make_float4((float)vi[3 * i], (float)vi[3 * i + 1], (float)vi[3 * i + 2], 0.f);
+    iC[k] = make_float4(vxh, vyh, vzh, 0.f);
+    iD[k] = make_float4((float)(vx - (double)vxh), (float)(vy - (double)vyh), (float)(vz - (double)vzh), 0.f);
 }
 
 // ---------------------------------------------------------------------------
@@ -277,6 +339,97 @@ __device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c)
 }
 
 // ---------------------------------------------------------------------------
+// j-memory order: where an i-particle sits among the j, and how close its neighbours are.
+//
+// The slots are kept in Morton order of the positions (host: rebuild_order).  Three things follow:
+//  * the force kernel for big i-blocks, whose i-particles are Morton-sorted too, can classify whole
+//    (warp of i) x (group of 32 j) blocks by their bounding boxes: FAR blocks take position differences
+//    from the hi parts alone, CLOSE blocks are evaluated in FP64 exactly as the reference does;
+//  * an open-addressing table id -> slot finds the j-particle an i-particle IS (same id), which is the
+//    only j its self-exclusion rule can apply to;
+//  * near2[slot] remembers the squared nearest-neighbour distance of every particle, which sets the
+//    radius inside which its pairs are evaluated in FP64 (the few close pairs that dominate acc and
+//    jerk and would otherwise carry the 2^-24 rounding of dx into a cancelling sum).
+// ---------------------------------------------------------------------------
+struct OrderInfo {
+    const u64 *hash;       // entries (id << 32 | slot + 2); 0 = empty; low word 1 = several slots carry this id
+    unsigned hash_mask;    // table size - 1 (a power of two); 0 = no table
+    const unsigned *keys;  // [nkeys] Morton keys of slots [0, nkeys), ascending
+    int nkeys;
+    float blo[3], binv[3]; // Morton grid: cell = (x - blo) * binv, 1024 cells per axis (x relative to x0)
+    float cap2;            // upper bound of the close radius squared
+    float kclose;          // K: pairs closer than sqrt(K) x (nearest-neighbour distance) go to FP64; 0 = off
+    float farc2;           // FAR blocks: box gap^2 > farc2 * (largest |coordinate|)^2
+};
+
+__device__ __forceinline__ unsigned hash_id(int id)
+{
+    unsigned h = (unsigned)id * 2654435761u;
+    return h ^ (h >> 15);
+}
+// slot of the j-particle with this id: >= 0, -1 = none, -2 = several
+__device__ __forceinline__ int hash_lookup(const OrderInfo &o, const int id)
+{
+    if (o.hash_mask == 0u) return -1;
+    unsigned h = hash_id(id) & o.hash_mask;
+    for (unsigned probe = 0; probe <= o.hash_mask; probe++) {
+        const u64 e = o.hash[h];
+        if (e == 0ull) return -1;
+        if ((int)(unsigned)(e >> 32) == id) {
+            const unsigned lowv = (unsigned)(e & 0xffffffffu);
+            return lowv == 1u ? -2 : (int)lowv - 2;
+        }
+        h = (h + 1u) & o.hash_mask;
+    }
+    return -1;
+}
+__global__ void hash_insert_kernel(const int n, const JState s, u64 *table, const unsigned mask)
+{
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= n) return;
+    if (!(s.q[6][slot].y > (double)TINYF)) return;   // massless / unset slots exert no force: nothing to exclude
+    const int id = s.ia[slot].x;
+    const u64 mine = ((u64)(unsigned)id << 32) | (u64)(unsigned)(slot + 2);
+    unsigned h = hash_id(id) & mask;
+    for (unsigned probe = 0; probe <= mask; probe++) {
+        const u64 old = atomicCAS(&table[h], 0ull, mine);
+        if (old == 0ull) return;
+        if ((int)(unsigned)(old >> 32) == id) {   // a second slot with this id: the i-particles that carry it take
+            atomicExch(&table[h], ((u64)(unsigned)id << 32) | 1ull);   // the exact path for every j
+            return;
+        }
+        h = (h + 1u) & mask;
+    }
+}
+
+__device__ __forceinline__ unsigned spread3(unsigned v)   // 10 bits -> every third bit
+{
+    v = (v | (v << 16)) & 0x030000ffu;
+    v = (v | (v << 8)) & 0x0300f00fu;
+    v = (v | (v << 4)) & 0x030c30c3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+__device__ __forceinline__ unsigned morton30(const float x, const float y, const float z, const float *blo,
+                                             const float *binv)
+{
+    const float fx = fminf(fmaxf((x - blo[0]) * binv[0], 0.f), 1023.f);
+    const float fy = fminf(fmaxf((y - blo[1]) * binv[1], 0.f), 1023.f);
+    const float fz = fminf(fmaxf((z - blo[2]) * binv[2], 0.f), 1023.f);
+    return spread3((unsigned)fx) | (spread3((unsigned)fy) << 1) | (spread3((unsigned)fz) << 2);
+}
+// first slot whose key is >= key (binary search over the sorted keys), clamped to a valid slot
+__device__ __forceinline__ int key_search(const OrderInfo &o, const unsigned key)
+{
+    int lo = 0, hi = o.nkeys;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (o.keys[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    return lo < o.nkeys ? lo : o.nkeys - 1;
+}
+
+// ---------------------------------------------------------------------------
 // Force kernel.
 // ---------------------------------------------------------------------------
 // Arguments of the device-resident Hermite step (see "Device-resident Hermite block step" below).
@@ -284,11 +437,12 @@ struct HermiteArgs {
     int ni;
     const int *ilist;          // j-addresses of the active particles (mapped pinned host memory or device)
     const double *old_dt;      // their current time steps (same memory); unused by the init pass
-    int *ilist_d;              // device copies made by the gather pass, read by the corrector
+    const int *slot_of;        // address -> slot
+    int *ilist_d;              // device copies made by the gather pass (SLOTS), read by the corrector
     double *olddt_d;
     double tnext, eta;
     JState js;
-    float4 *iA, *iB, *iC;      // packed i-block for the force kernels
+    float4 *iA, *iB, *iC, *iD; // packed i-block for the force kernels
     double *pred;              // [ni][6] predicted pos, vel (FP64) kept for the corrector
     const double *sum;         // [ni][7] force-kernel output: acc, jerk, +sum m/r
     const int *nnid;           // [ni]
@@ -303,19 +457,27 @@ struct HermiteArgs {
 
 constexpr int MAX_PEERS = 7;   // other ranks of one NVSwitch domain (8 GPUs)
 struct ForceArgs {
-    const float4 *jA, *jB, *jC;   // predicted j (device)
-    const float4 *iA, *iB, *iC;   // packed i-block (device)
-    int ni, nj;                   // i count, j prefix [0, nj)
+    const float4 *jA, *jB, *jC;   // predicted j (device), offset to the first slot of this launch's j-window
+    const float4 *jG;             // group boxes, same offset (in groups)
+    const float4 *iA, *iB, *iC, *iD;   // packed i-block (device)
+    int ni, nj;                   // i count, j prefix [0, nj) of the window
     int tiles_per_split, nsplit;  // j decomposition over blockIdx.x
     int ni_pad;                   // stride of the partial workspace
-    int j_offset;                 // global address of local address 0
+    int j_offset;                 // added to the addresses reported in nearest-neighbour keys
+    int slot0;                    // first slot of the j-window (a multiple of TILE)
     int defer_reduce;             // 1: stop after the per-split partials (reduce_partials_kernel follows)
     float eps2;
+    const float4 *jL;             // lo parts of the predicted velocities and masses (FP64 pairs), same offset
+    JState js;                    // the whole j-memory (not offset): near2, predicted arrays by absolute slot
+    OrderInfo ord;
+    int *conf;                    // [ni] slot of the j-particle with particle i's id (-1 none, -2 several): read by the
+                                  // speculative kernel (near_kernel wrote it), written by the masked kernels
+    const int *iperm;             // outputs of packed particle i go to index iperm[i] (NULL: i)
     double *part_sum;             // [nsplit][ni_pad][7]
-    u64 *part_key;                // [nsplit][ni_pad]
+    u64 *part_key;                // [nsplit][ni_pad]   (min r2 bits << 32 | slot)
     unsigned int *tickets;        // [gridDim.y], zero between launches
     double *out_sum;              // [ni][7]: acc xyz, jerk xyz, +sum m/r
-    u64 *out_key;                 // [ni]
+    u64 *out_key;                 // [ni]   (min r2 bits << 32 | reported address)
     int *out_nnid;                // [ni]
     int *ngb_cnt;                 // [ni]   (LIST only; zeroed by the host)
     int *ngb_list;                // [ni][ngb_cap]
@@ -326,9 +488,9 @@ struct ForceArgs {
     unsigned long long *host_flag;       // mapped pinned host memory (NULL: no signal)
     unsigned long long flag_seq;         // value to write
     unsigned int done_expected;          // CTAs that write final outputs in this launch
-    // multi-GPU exchange fused into the force kernel: whoever writes final outputs of this rank's
-    // j-shard also stores them into its slot of every peer's exchange buffer over NVLink (peer pointers
-    // from CUDA IPC), so the partials travel while the other i-blocks are still being computed
+    // multi-GPU exchange fused into the force kernel: whoever writes final outputs of this device's
+    // j-shard also stores them into its slot of every peer's exchange buffer over NVLink (peer pointers),
+    // so the partials travel while the other i-blocks are still being computed
     // device-resident Hermite step, small blocks: whoever writes particle i's final force also runs its
     // corrector (HERM kernels), so a block step is two launches (predict+gather, force+correct)
     HermiteArgs herm;
@@ -339,32 +501,42 @@ struct ForceArgs {
 };
 
 // i-block carried in the kernel parameters (constant bank) for small i-blocks: no H2D copy at all.
-// Layout [3][N]: iA, iB, iC.  N == 0 is a 48-byte dummy.
+// Layout [4][N]: iA, iB, iC, iD.  N == 0 is a 64-byte dummy.
 template <int N>
 struct InlineI {
-    float4 d[3 * (N > 0 ? N : 1)];
+    float4 d[4 * (N > 0 ? N : 1)];
 };
 
 __device__ __forceinline__ void hermite_correct_one(const HermiteArgs &h, const int i, const double *f, const int nnid);
 
-// Final outputs of particle i (local arrays + the peers' exchange slots).
+// Final outputs of particle i (local arrays + the peers' exchange slots).  kk carries a slot of this
+// launch's j-window; what leaves the kernel carries the address the caller gave that particle.
 template <bool NN, bool HERM = false>
 __device__ __forceinline__ void store_outputs(const ForceArgs &p, const int i, const double *tot, const u64 kk)
 {
     int id = -1;
-    if (NN && kk != KEY_NONE) id = __float_as_int(p.jB[(int)(unsigned)(kk & 0xffffffffu) - p.j_offset].w);
+    u64 ko = KEY_NONE;
+    if (NN && kk != KEY_NONE) {
+        const int sl = (int)(unsigned)(kk & 0xffffffffu);
+        id = __float_as_int(p.jB[sl].w);
+        ko = (kk & 0xffffffff00000000ull) | (u64)(unsigned)(__float_as_int(p.jC[sl].w) + p.j_offset);
+        // remember how close this particle's nearest neighbour is (sets its FP64 radius next time)
+        const int me = p.conf ? p.conf[i] : -1;
+        if (me >= 0) p.js.near2[me] = __int_as_float((int)(unsigned)(kk >> 32));
+    }
     if (HERM) {   // the particle's force is complete: correct it right here
         hermite_correct_one(p.herm, i, tot, id);
     } else {
+        const int io = p.iperm ? p.iperm[i] : i;
 #pragma unroll
-        for (int q = 0; q < 7; q++) p.out_sum[(size_t)i * 7 + q] = tot[q];
-        p.out_key[i] = kk;
-        if (NN) p.out_nnid[i] = id;
+        for (int q = 0; q < 7; q++) p.out_sum[(size_t)io * 7 + q] = tot[q];
+        p.out_key[io] = ko;
+        if (NN) p.out_nnid[io] = id;
         for (int m = 0; m < p.n_mirror; m++) {
 #pragma unroll
-            for (int q = 0; q < 7; q++) p.m_sum[m][(size_t)i * 7 + q] = tot[q];
-            p.m_key[m][i] = kk;
-            p.m_id[m][i] = id;
+            for (int q = 0; q < 7; q++) p.m_sum[m][(size_t)io * 7 + q] = tot[q];
+            p.m_key[m][io] = ko;
+            p.m_id[m][io] = id;
         }
     }
 }
@@ -389,6 +561,43 @@ __device__ __forceinline__ void signal_done(const ForceArgs &p)
     }
 }
 
+// ---- FP64 pairs -------------------------------------------------------------------------------
+// One (i, j) interaction with the reference's FP64 expression tree (idata.cc:206-233) on the double-single
+// predicted j (positions A+B, velocities C+L, mass A.w+L.w: 48 bits each) and the double-single i-particle.
+// Returns acc, jerk, +m/r.
+struct F64Out {
+    double v[7];
+};
+__device__ __forceinline__ void fp64_accumulate(double *v, const double dx, const double dy, const double dz,
+                                                const double dvx, const double dvy, const double dvz, const double m,
+                                                const double eps2t)
+{
+    const double r2 = dx * dx + dy * dy + dz * dz;
+    const double xv = dx * dvx + dy * dvy + dz * dvz;
+    const double ri = rsqrt(r2 + eps2t);      // eps2t = eps2 + 2^-52 (idata.cc:216)
+    const double r2i = ri * ri;
+    const double mri = m * ri;
+    const double mr3i = mri * r2i;
+    const double a3 = -3.0 * xv * r2i;
+    v[0] += mr3i * dx;
+    v[1] += mr3i * dy;
+    v[2] += mr3i * dz;
+    v[3] += mr3i * (dvx + a3 * dx);
+    v[4] += mr3i * (dvy + a3 * dy);
+    v[5] += mr3i * (dvz + a3 * dz);
+    if (r2 > (double)TINYF) v[6] += mri;
+}
+__device__ __noinline__ void fp64_pair(F64Out *o, const float4 a, const float4 b, const float4 c, const float4 l,
+                                       const double xi, const double yi, const double zi, const double vxi,
+                                       const double vyi, const double vzi, const double eps2t)
+{
+#pragma unroll
+    for (int q = 0; q < 7; q++) o->v[q] = 0.0;
+    fp64_accumulate(o->v, ((double)a.x + (double)b.x) - xi, ((double)a.y + (double)b.y) - yi,
+                    ((double)a.z + (double)b.z) - zi, ((double)c.x + (double)l.x) - vxi, ((double)c.y + (double)l.y) - vyi,
+                    ((double)c.z + (double)l.z) - vzi, (double)a.w + (double)l.w, eps2t);
+}
+
 struct Acc7 {
     float ax, ay, az, jx, jy, jz, pot;
 };
@@ -396,11 +605,12 @@ struct Acc7 {
 // One (i, j) interaction in scalar FP32 with double-single positions.
 // 9 FADD (DS dx) + 3 FADD (dv) + 6 FMUL/FFMA (r2, xv) + 1 FADD (eps2) + MUFU.RSQ
 // + 5 FMUL + 9 FFMA + 1 FADD, plus guards.  Counted as 60 flop by convention
-// (src/amuse_ph4/src/jdata.cc:1038).
+// (src/amuse_ph4/src/jdata.cc:1038).  Returns true if the pair is closer than the i-particle's FP64
+// radius: it is then left out of the FP32 sums and the caller evaluates it with fp64_pair.
 template <bool NN, bool LIST, bool NR>
-__device__ __forceinline__ void interact(const float4 a, const float4 b, const float4 c, int jaddr, float xh,
+__device__ __forceinline__ bool interact(const float4 a, const float4 b, const float4 c, int jaddr, float xh,
                                          float yh, float zh, float xl, float yl, float zl, float vx, float vy,
-                                         float vz, int iid, float h2, float eps2, Acc7 &s, float &r2min,
+                                         float vz, int iid, float h2, float eps2, float thr, Acc7 &s, float &r2min,
                                          int &jmin, int i_global, const ForceArgs &p)
 {
     float dx = (a.x - xh) + (b.x - xl);
@@ -413,8 +623,10 @@ __device__ __forceinline__ void interact(const float4 a, const float4 b, const f
     // neighbour search are guarded by r2 > TINY.  Equal ids are skipped altogether (g6 rule).
     const bool idok = (__float_as_int(b.w) != iid);
     const bool ok = idok && (r2 > TINYF);
+    const bool hp = ok && (r2 < thr);
+    const bool use = idok && !hp;
     float rinv = NR ? rsqrt_refined(r2 + eps2) : rsqrt_approx(r2 + eps2);   // eps2 holds eps2 + TINY
-    rinv = idok ? rinv : 0.f;
+    rinv = use ? rinv : 0.f;
     float rinv2 = rinv * rinv;
     float mrinv = a.w * rinv;
     float mr3 = mrinv * rinv2;
@@ -425,7 +637,7 @@ __device__ __forceinline__ void interact(const float4 a, const float4 b, const f
     s.jx = fmaf(mr3, fmaf(a3, dx, dvx), s.jx);
     s.jy = fmaf(mr3, fmaf(a3, dy, dvy), s.jy);
     s.jz = fmaf(mr3, fmaf(a3, dz, dvz), s.jz);
-    s.pot += ok ? mrinv : 0.f;
+    s.pot += (ok && !hp) ? mrinv : 0.f;
     if (NN) {
         float r2n = ok ? r2 : __int_as_float(0x7f800000);
         if (r2n < r2min) {
@@ -439,6 +651,7 @@ __device__ __forceinline__ void interact(const float4 a, const float4 b, const f
             if (pos < p.ngb_cap) p.ngb_list[(size_t)i_global * p.ngb_cap + pos] = __float_as_int(b.w);
         }
     }
+    return hp;
 }
 
 // Two i-particles at once with Blackwell's packed FP32 pipe (FADD2/FMUL2/FFMA2):
@@ -453,10 +666,11 @@ struct Acc7P {
     u64 ax, ay, az, jx, jy, jz, pot;
 };
 
+// returns bit 0 / bit 1: pair (i0, j) / (i1, j) is inside the FP64 radius and was left out of the sums
 template <bool NN, bool LIST, bool NR, bool TRACKJ = true>
-__device__ __forceinline__ void interact2(const float4 a, const float4 b, const float4 c, int jaddr, const IPair &I,
-                                          u64 eps2p, Acc7P &s, float &r2min0, int &jmin0, float &r2min1,
-                                          int &jmin1, int i_global0, const ForceArgs &p)
+__device__ __forceinline__ int interact2(const float4 a, const float4 b, const float4 c, int jaddr, const IPair &I,
+                                         u64 eps2p, const float thr0, const float thr1, Acc7P &s, float &r2min0,
+                                         int &jmin0, float &r2min1, int &jmin1, int i_global0, const ForceArgs &p)
 {
     u64 dx = add2(add2(pk(a.x, a.x), I.nxh), add2(pk(b.x, b.x), I.nxl));
     u64 dy = add2(add2(pk(a.y, a.y), I.nyh), add2(pk(b.y, b.y), I.nyl));
@@ -473,6 +687,7 @@ __device__ __forceinline__ void interact2(const float4 a, const float4 b, const 
     int jid = __float_as_int(b.w);
     const bool id0 = (jid != I.id0), id1 = (jid != I.id1);
     const bool ok0 = id0 && (r20 > TINYF), ok1 = id1 && (r21 > TINYF);
+    const bool hp0 = ok0 && (r20 < thr0), hp1 = ok1 && (r21 < thr1);
     float ri0 = rsqrt_approx(e0);
     float ri1 = rsqrt_approx(e1);
     u64 rinv = pk(ri0, ri1);
@@ -481,7 +696,7 @@ __device__ __forceinline__ void interact2(const float4 a, const float4 b, const 
         rinv = fma2(mul2(rinv, pk(-0.5f, -0.5f)), e, rinv);
         upk(rinv, ri0, ri1);
     }
-    rinv = pk(id0 ? ri0 : 0.f, id1 ? ri1 : 0.f);
+    rinv = pk((id0 && !hp0) ? ri0 : 0.f, (id1 && !hp1) ? ri1 : 0.f);
     u64 rinv2 = mul2(rinv, rinv);
     u64 mrinv = mul2(pk(a.w, a.w), rinv);
     u64 mr3 = mul2(mrinv, rinv2);
@@ -492,11 +707,11 @@ __device__ __forceinline__ void interact2(const float4 a, const float4 b, const 
     s.jx = fma2(mr3, fma2(a3, dx, dvx), s.jx);
     s.jy = fma2(mr3, fma2(a3, dy, dvy), s.jy);
     s.jz = fma2(mr3, fma2(a3, dz, dvz), s.jz);
-    s.pot = fma2(pk(a.w, a.w), pk(ok0 ? ri0 : 0.f, ok1 ? ri1 : 0.f), s.pot);
+    s.pot = fma2(pk(a.w, a.w), pk((ok0 && !hp0) ? ri0 : 0.f, (ok1 && !hp1) ? ri1 : 0.f), s.pot);
     if (NN) {
         float n0 = ok0 ? r20 : __int_as_float(0x7f800000);
         float n1 = ok1 ? r21 : __int_as_float(0x7f800000);
-        if (!TRACKJ) {   // the speculative kernel keeps only the minimum and finds j afterwards
+        if (!TRACKJ) {
             r2min0 = fminf(r2min0, n0);
             r2min1 = fminf(r2min1, n1);
         } else {
@@ -520,6 +735,28 @@ __device__ __forceinline__ void interact2(const float4 a, const float4 b, const 
             if (pos < p.ngb_cap) p.ngb_list[(size_t)(i_global0 + 1) * p.ngb_cap + pos] = jid;
         }
     }
+    return (hp0 ? 1 : 0) | (hp1 ? 2 : 0);
+}
+
+// Where particle i sits among the j and how large its FP64 radius is (masked kernels, per i-particle):
+// the j-particle with its id if there is exactly one (the usual case: the active particles of a block
+// step ARE j-particles), else the slot its Morton key falls on.  d = distance to that slot + that
+// particle's own nearest-neighbour distance bounds i's nearest-neighbour distance from above.
+__device__ __forceinline__ float close_radius2(const ForceArgs &p, const int iid, const float xh, const float yh,
+                                               const float zh, const float xl, const float yl, const float zl,
+                                               int &self_slot)
+{
+    self_slot = hash_lookup(p.ord, iid);
+    if (!(p.ord.kclose > 0.f)) return 0.f;
+    int s = self_slot;
+    if (s < 0) {
+        if (p.ord.nkeys <= 0) return 0.f;
+        s = key_search(p.ord, morton30(xh, yh, zh, p.ord.blo, p.ord.binv));
+    }
+    const float4 a = p.js.A[s], b = p.js.B[s];
+    const float dx = (a.x - xh) + (b.x - xl), dy = (a.y - yh) + (b.y - yl), dz = (a.z - zh) + (b.z - zl);
+    const float d = sqrtf(dx * dx + dy * dy + dz * dz) + sqrtf(p.js.near2[s]);
+    return fminf(p.ord.kclose * d * d, p.ord.cap2);
 }
 
 // Split reduction shared by the force kernels: the last CTA of an i-block (ticket) sums the
@@ -631,13 +868,14 @@ struct __align__(16) ForceSmem {
     float4 A[STAGES][TILE];
     float4 B[STAGES][TILE];
     float4 C[STAGES][TILE];
+    float4 G[STAGES][TBOX];   // group boxes + tile box (speculative kernel only)
     uint64_t full[STAGES];
     unsigned int is_last;
 };
 
-__device__ __forceinline__ u64 make_key(float r2min, int jmin_global)
+__device__ __forceinline__ u64 make_key(float r2min, int jmin)
 {
-    return ((u64)(unsigned)__float_as_int(r2min) << 32) | (u64)(unsigned)jmin_global;
+    return ((u64)(unsigned)__float_as_int(r2min) << 32) | (u64)(unsigned)jmin;
 }
 
 // Thread layout: tid = jslot * NI_SLOTS + islot.  A CTA owns IB = NI_SLOTS*IPT
@@ -645,11 +883,12 @@ __device__ __forceinline__ u64 make_key(float r2min, int jmin_global)
 // of split blockIdx.x; inside a tile the NJ_SLOTS = THREADS/NI_SLOTS j-slots take
 // interleaved j.  i-particles stay in registers for the whole kernel; j tiles
 // arrive by TMA bulk copies (3 per stage) signalled on an mbarrier; per-tile FP32
-// partial sums are flushed to FP64 so that long sums keep ~1e-7 accuracy.
+// partial sums are flushed to FP64 so that long sums keep ~1e-7 accuracy; pairs inside the
+// i-particle's FP64 radius bypass the FP32 sums altogether (fp64_pair).
 // Partials of the j-slots are reduced with warp shuffles + shared memory, and the
 // partials of the j-splits by the last CTA to arrive (ticket), in fixed order.
 template <int IPT, int NI_SLOTS, bool NN, bool LIST, bool PACKED, bool NR, int MINB, int INL, bool HERM = false>
-__global__ void __launch_bounds__(THREADS, MINB) force_kernel(const ForceArgs p,
+__global__ void __launch_bounds__(THREADS, MINB) force_kernel(const __grid_constant__ ForceArgs p,
                                                               const __grid_constant__ InlineI<INL> ii)
 {
     constexpr int NJ_SLOTS = THREADS / NI_SLOTS;
@@ -691,12 +930,14 @@ __global__ void __launch_bounds__(THREADS, MINB) force_kernel(const ForceArgs p,
     }
 
     // ---- register-resident i-particles -----------------------------------
-    float xh[IPT], yh[IPT], zh[IPT], xl[IPT], yl[IPT], zl[IPT], vx[IPT], vy[IPT], vz[IPT], h2[IPT];
+    auto i_of = [&](int k) -> int {
+        return PACKED ? (int)(blockIdx.y * IB + (islot * 2 + (k & 1)) + (k >> 1) * (2 * NI_SLOTS)) : i_base + k * NI_SLOTS;
+    };
+    float xh[IPT], yh[IPT], zh[IPT], xl[IPT], yl[IPT], zl[IPT], vx[IPT], vy[IPT], vz[IPT], h2[IPT], thr[IPT];
     int iid[IPT];
 #pragma unroll
     for (int k = 0; k < IPT; k++) {
-        int i = i_base + k * NI_SLOTS;
-        if (PACKED) i = blockIdx.y * IB + (islot * 2 + (k & 1)) + (k >> 1) * (2 * NI_SLOTS);
+        const int i = i_of(k);
         float4 a = make_float4(0.f, 0.f, 0.f, -1.f), b = make_float4(0.f, 0.f, 0.f, __int_as_float(0x80000000)),
                c = make_float4(0.f, 0.f, 0.f, 0.f);
         if (i < p.ni) {
@@ -713,9 +954,24 @@ __global__ void __launch_bounds__(THREADS, MINB) force_kernel(const ForceArgs p,
         xh[k] = a.x; yh[k] = a.y; zh[k] = a.z; h2[k] = a.w;
         xl[k] = b.x; yl[k] = b.y; zl[k] = b.z; iid[k] = __float_as_int(b.w);
         vx[k] = c.x; vy[k] = c.y; vz[k] = c.z;
+        thr[k] = 0.f;
+        if (i < p.ni) {
+            int self_slot;
+            thr[k] = close_radius2(p, iid[k], xh[k], yh[k], zh[k], xl[k], yl[k], zl[k], self_slot);
+            if (p.conf && blockIdx.x == 0 && jslot == 0) p.conf[i] = self_slot;
+        }
     }
-    auto i_of = [&](int k) -> int {
-        return PACKED ? (int)(blockIdx.y * IB + (islot * 2 + (k & 1)) + (k >> 1) * (2 * NI_SLOTS)) : i_base + k * NI_SLOTS;
+    const double eps2t = (double)p.eps2 + (double)TINYF;
+    // pair (k, slot j of this launch's window) in FP64, added to D[k] (rare: a handful of pairs per particle)
+    auto close_pair = [&](const int k, const float4 a, const float4 b, const float4 c, const int jlocal, double *Dk) {
+        const int i = i_of(k);
+        const float4 d = (INL > 0) ? ii.d[3 * INL + i] : p.iD[i];
+        F64Out o;
+        fp64_pair(&o, a, b, c, p.jL[jlocal], (double)xh[k] + (double)xl[k], (double)yh[k] + (double)yl[k],
+                  (double)zh[k] + (double)zl[k], (double)vx[k] + (double)d.x, (double)vy[k] + (double)d.y,
+                  (double)vz[k] + (double)d.z, eps2t);
+#pragma unroll
+        for (int q = 0; q < 7; q++) Dk[q] += o.v[q];
     };
 
     double D[IPT][7];
@@ -781,9 +1037,12 @@ __global__ void __launch_bounds__(THREADS, MINB) force_kernel(const ForceArgs p,
                     const float4 a = tA[jj], b = tB[jj], c = tC[jj];
                     const int jaddr = jtile + jj;
 #pragma unroll
-                    for (int k = 0; k < IPT; k++)
-                        interact<NN, LIST, NR>(a, b, c, jaddr, xh[k], yh[k], zh[k], xl[k], yl[k], zl[k], vx[k], vy[k],
-                                               vz[k], iid[k], h2[k], eps2, S[k], r2min[k], jmin[k], i_of(k), p);
+                    for (int k = 0; k < IPT; k++) {
+                        const bool hp = interact<NN, LIST, NR>(a, b, c, jaddr, xh[k], yh[k], zh[k], xl[k], yl[k], zl[k],
+                                                               vx[k], vy[k], vz[k], iid[k], h2[k], eps2, thr[k], S[k],
+                                                               r2min[k], jmin[k], i_of(k), p);
+                        if (hp) close_pair(k, a, b, c, jaddr, D[k]);
+                    }
                 };
                 if (whole) {
 #pragma unroll UNROLL
@@ -805,9 +1064,15 @@ __global__ void __launch_bounds__(THREADS, MINB) force_kernel(const ForceArgs p,
                     const float4 a = tA[jj], b = tB[jj], c = tC[jj];
                     const int jaddr = jtile + jj;
 #pragma unroll
-                    for (int q = 0; q < NP; q++)
-                        interact2<NN, LIST, NR>(a, b, c, jaddr, IP[q], eps2p, S[q], r2min[2 * q], jmin[2 * q],
-                                                r2min[2 * q + 1], jmin[2 * q + 1], i_of(2 * q), p);
+                    for (int q = 0; q < NP; q++) {
+                        const int hpm = interact2<NN, LIST, NR>(a, b, c, jaddr, IP[q], eps2p, thr[2 * q], thr[2 * q + 1],
+                                                                S[q], r2min[2 * q], jmin[2 * q], r2min[2 * q + 1],
+                                                                jmin[2 * q + 1], i_of(2 * q), p);
+                        if (hpm) {
+                            if (hpm & 1) close_pair(2 * q, a, b, c, jaddr, D[2 * q]);
+                            if (hpm & 2) close_pair(2 * q + 1, a, b, c, jaddr, D[2 * q + 1]);
+                        }
+                    }
                 };
                 if (whole) {
 #pragma unroll UNROLL
@@ -839,11 +1104,11 @@ __global__ void __launch_bounds__(THREADS, MINB) force_kernel(const ForceArgs p,
         }
     }
 
-    // ---- keys ---------------------------------------------------------------
+    // ---- keys (slot of this launch's j-window) --------------------------------
     u64 key[IPT];
 #pragma unroll
     for (int k = 0; k < IPT; k++)
-        key[k] = (jmin[k] >= 0) ? make_key(r2min[k], jmin[k] + p.j_offset) : KEY_NONE;
+        key[k] = (jmin[k] >= 0 && r2min[k] < 1.0e30f) ? make_key(r2min[k], jmin[k]) : KEY_NONE;   // >= 1e30: parked slots
 
     // ---- reduce over the j-slots of this CTA -------------------------------
     double *red = reinterpret_cast<double *>(smem_raw);  // tile buffers are dead now
@@ -916,22 +1181,25 @@ __global__ void __launch_bounds__(THREADS, MINB) force_kernel(const ForceArgs p,
 }
 
 // ---------------------------------------------------------------------------
-// Speculative force kernel (large i-blocks, packed FP32).
+// Speculative force kernel (large i-blocks, packed FP32), round 2.
 //
-// The masks of the exact pair rule (skip equal ids; pot and the neighbour search only for
-// r2 > 2^-52) cost ~18 ALU-pipe instructions per packed pair and, on this chip, compete with the
-// FMA pipe for register-file read bandwidth (profiles/: FFMA2 with three distinct register
-// operands runs at 2/3 rate).  Almost no pair needs them, so the j stream is processed in groups
-// of GRP pairs WITHOUT masks, and each group is verified afterwards:
-//   * an equal-id pair can only occur in a tile whose id range [C[0].w, C[1].w] (written by
-//     predict_kernel) contains the id of one of the warp's i-particles -> such tiles take the
-//     masked path from the start;
-//   * a pair with r2 <= 2^-52 shows up in the running minimum of r2, which is tracked anyway for
-//     the nearest neighbour -> the group's FP32 partial sums are discarded and the group is redone
-//     with the masked pair function.
-// Results are therefore those of the masked rule for every input.  The nearest neighbour is kept
-// as (min r2, first group that lowered it) with one 3-input FMNMX per i per two j; the exact j is
-// found at the end by re-scanning that one group with the same r2 instruction sequence.
+// i-particles arrive Morton-sorted (64 consecutive ones per warp, two per thread), the j-memory is
+// Morton-ordered, and predict_kernel has left a bounding box per group of 32 j and per tile.  Every
+// (warp, group) block is classified by box distance, warp-uniformly:
+//   FAR    gap^2 > max(farc2 * (largest |coordinate|)^2, every i's nearest-neighbour bound, every i's FP64
+//          radius): position differences from the hi parts alone (31 packed FP32 operations per pair
+//          instead of 37; the lo parts are below the rounding of such a difference), no neighbour search;
+//   NEAR   mask-free pair function on the double-single differences, running minimum of r2 for the
+//          neighbour search; a group whose minimum is not above R2_EXACT is redone exactly;
+//   CLOSE  some particle of the warp has the group's box inside its FP64 radius, or the j-particle that
+//          carries the id of one of the warp's particles sits in the group (conf[], from the id table), or
+//          the group is the ragged tail: the whole block is evaluated in FP64 exactly as the reference does
+//          (idata.cc:206-233: equal ids skipped, pot and neighbour search only for r2 > 2^-52), each lane
+//          predicting one j from the FP64 state and broadcasting it by shuffles.
+// Results are therefore those of the masked rule for every input, and the pairs that dominate a
+// particle's acc and jerk never see FP32 rounding.  The nearest neighbour is kept as (min r2, first group
+// that lowered it); the exact j is found at the end by re-scanning that one group with the same r2
+// instruction sequence.
 // ---------------------------------------------------------------------------
 #ifndef G6_GRP
 #define G6_GRP 32
@@ -939,11 +1207,9 @@ __global__ void __launch_bounds__(THREADS, MINB) force_kernel(const ForceArgs p,
 #ifndef G6_FUNROLL
 #define G6_FUNROLL 2
 #endif
-#ifndef G6_DUAL
-#define G6_DUAL 0   // 0: one FP32 partial-sum set per group; k: two sets (even/odd j) in kernels with IPT >= k
-#endif
-constexpr int GRP = G6_GRP;   // pairs per speculation/flush group (FP32 partial sums span one group)
+constexpr int GRP = G6_GRP;   // pairs per group (FP32 partial sums span one group); one lane per j in the FP64 path
 constexpr int FUNROLL = G6_FUNROLL;  // j-pairs unrolled in the mask-free loop
+static_assert(GRP == 32, "the FP64 path predicts one j per lane");
 
 __device__ __forceinline__ float min3f(float a, float b, float c)
 {
@@ -952,7 +1218,7 @@ __device__ __forceinline__ float min3f(float a, float b, float c)
     return d;
 }
 
-// Geometry shared by the fast path, the masked path and the neighbour re-scan: identical
+// Geometry shared by the fast path, the FP64 path's neighbour search and the neighbour re-scan: identical
 // instruction sequence, so r2 is bit-identical in all three.
 __device__ __forceinline__ void pair_geometry(const float4 a, const float4 b, const IPair &I, u64 &dx, u64 &dy, u64 &dz,
                                               u64 &r2)
@@ -963,16 +1229,23 @@ __device__ __forceinline__ void pair_geometry(const float4 a, const float4 b, co
     r2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
 }
 
-// One j against an i-pair, no masks: 38 packed FP32 operations + 2 MUFU.  Accumulates -acc, -jerk, +pot.
+// One j against an i-pair, no masks: 37 (FAR: 31) packed FP32 operations + 2 MUFU.  Accumulates -acc, -jerk, +pot.
 // EPS0: the caller runs unsoftened (eps2 = 0, ph4's AMUSE default).  The reference still adds 2^-52 to r2
 // (idata.cc:216); in FP32 that add is the identity for r2 > 2^-26, so it is skipped here and the group
 // verification (running minimum of r2) redoes any group that holds a closer pair with the exact path.
-template <bool NR, bool EPS0>
+template <bool NR, bool EPS0, bool FAR>
 __device__ __forceinline__ u64 interact2_fast(const float4 a, const float4 b, const float4 c, const IPair &I,
                                               const u64 eps2p, Acc7P &s)
 {
     u64 dx, dy, dz, r2;
-    pair_geometry(a, b, I, dx, dy, dz, r2);
+    if (FAR) {
+        dx = add2(pk(a.x, a.x), I.nxh);
+        dy = add2(pk(a.y, a.y), I.nyh);
+        dz = add2(pk(a.z, a.z), I.nzh);
+        r2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
+    } else {
+        pair_geometry(a, b, I, dx, dy, dz, r2);
+    }
     const u64 dvx = add2(pk(c.x, c.x), I.nvx);
     const u64 dvy = add2(pk(c.y, c.y), I.nvy);
     const u64 dvz = add2(pk(c.z, c.z), I.nvz);
@@ -1010,17 +1283,107 @@ __device__ __forceinline__ u64 interact2_fast(const float4 a, const float4 b, co
     return r2;
 }
 
+// FP64 evaluation of one group of up to 32 j against one packed i-pair (CLOSE blocks).  Lane l converts
+// j = first + l of the tile to doubles and the warp walks the group by shuffles.
+// Not inlined: its registers must not weigh on the FP32 loop.
+struct F64Group {
+    double v[2][7];
+    float rmin[2];
+};
+__device__ __noinline__ void fp64_group(F64Group *o, const ForceArgs *p, const int jfirst, const int count,
+                                        const float4 *tA, const float4 *tB, const float4 *tC, const IPair ip,
+                                        const int i0)
+{
+    const int lane = threadIdx.x & 31;
+    const float4 ja = tA[lane], jb = tB[lane], jc = tC[lane];
+    const float4 jl = p->jL[jfirst + lane];   // inside the padded arrays even when lane >= count
+    const int myid = __float_as_int(jb.w);
+    const double mym = (lane < count && ja.w > 0.f) ? (double)ja.w + (double)jl.w : 0.0;   // massless j: skipped (idata.cc:208)
+    const double mx = (double)ja.x + (double)jb.x, my = (double)ja.y + (double)jb.y, mz = (double)ja.z + (double)jb.z;
+    const double mvx = (double)jc.x + (double)jl.x, mvy = (double)jc.y + (double)jl.y, mvz = (double)jc.z + (double)jl.z;
+    float h0, h1, l0, l1;
+    double xi[2], yi[2], zi[2], vxi[2], vyi[2], vzi[2];
+    upk(ip.nxh, h0, h1); upk(ip.nxl, l0, l1); xi[0] = -((double)h0 + (double)l0); xi[1] = -((double)h1 + (double)l1);
+    upk(ip.nyh, h0, h1); upk(ip.nyl, l0, l1); yi[0] = -((double)h0 + (double)l0); yi[1] = -((double)h1 + (double)l1);
+    upk(ip.nzh, h0, h1); upk(ip.nzl, l0, l1); zi[0] = -((double)h0 + (double)l0); zi[1] = -((double)h1 + (double)l1);
+    const float4 d0 = (i0 < p->ni) ? p->iD[i0] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 d1 = (i0 + 1 < p->ni) ? p->iD[i0 + 1] : make_float4(0.f, 0.f, 0.f, 0.f);
+    upk(ip.nvx, h0, h1); vxi[0] = (double)d0.x - (double)h0; vxi[1] = (double)d1.x - (double)h1;
+    upk(ip.nvy, h0, h1); vyi[0] = (double)d0.y - (double)h0; vyi[1] = (double)d1.y - (double)h1;
+    upk(ip.nvz, h0, h1); vzi[0] = (double)d0.z - (double)h0; vzi[1] = (double)d1.z - (double)h1;
+    const double eps2t = (double)p->eps2 + (double)TINYF;
+    double v0[7] = {0, 0, 0, 0, 0, 0, 0}, v1[7] = {0, 0, 0, 0, 0, 0, 0};
+    float rm0 = __int_as_float(0x7f800000), rm1 = rm0;
+    for (int u = 0; u < count; u++) {
+        const double m = __shfl_sync(0xffffffffu, mym, u);
+        if (m == 0.0) continue;   // warp-uniform
+        const double xj = __shfl_sync(0xffffffffu, mx, u), yj = __shfl_sync(0xffffffffu, my, u),
+                     zj = __shfl_sync(0xffffffffu, mz, u);
+        const double vxj = __shfl_sync(0xffffffffu, mvx, u), vyj = __shfl_sync(0xffffffffu, mvy, u),
+                     vzj = __shfl_sync(0xffffffffu, mvz, u);
+        const int jid = __shfl_sync(0xffffffffu, myid, u);
+        // neighbour search on the FP32 r2 every other path uses
+        u64 dx, dy, dz, r2;
+        pair_geometry(tA[u], tB[u], ip, dx, dy, dz, r2);
+        float r20, r21;
+        upk(r2, r20, r21);
+        if (jid != ip.id0) {
+            if (r20 > TINYF) rm0 = fminf(rm0, r20);
+            fp64_accumulate(v0, xj - xi[0], yj - yi[0], zj - zi[0], vxj - vxi[0], vyj - vyi[0], vzj - vzi[0], m, eps2t);
+        }
+        if (jid != ip.id1) {
+            if (r21 > TINYF) rm1 = fminf(rm1, r21);
+            fp64_accumulate(v1, xj - xi[1], yj - yi[1], zj - zi[1], vxj - vxi[1], vyj - vyi[1], vzj - vzi[1], m, eps2t);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 7; q++) {
+        o->v[0][q] = v0[q];
+        o->v[1][q] = v1[q];
+    }
+    o->rmin[0] = rm0;
+    o->rmin[1] = rm1;
+}
+
+// Pre-pass of the speculative kernel, one thread per packed i-particle: the slot of the j-particle that
+// carries its id (conf[]) and a strict upper bound of its nearest-neighbour distance (iD.w) -- the
+// smallest distance to the 2W predicted j around its place in the Morton order.
+__global__ void __launch_bounds__(256) near_kernel(const ForceArgs p, const int W)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.ni) return;
+    const float4 a = p.iA[i], b = p.iB[i];
+    const int iid = __float_as_int(b.w);
+    const int self = hash_lookup(p.ord, iid);
+    p.conf[i] = self;
+    float d2 = __int_as_float(0x7f800000);
+    if (p.ord.nkeys > 0) {
+        int s = self;
+        if (s < 0 || s >= p.ord.nkeys) s = key_search(p.ord, morton30(a.x, a.y, a.z, p.ord.blo, p.ord.binv));
+        const int lo = max(0, s - W), hi = min(p.ord.nkeys, s + W + 1);
+        for (int j = lo; j < hi; j++) {
+            const float4 ja = p.js.A[j], jb = p.js.B[j];
+            const float dx = (ja.x - a.x) + (jb.x - b.x), dy = (ja.y - a.y) + (jb.y - b.y), dz = (ja.z - a.z) + (jb.z - b.z);
+            const float r2 = dx * dx + dy * dy + dz * dz;
+            if (ja.w > 0.f && __float_as_int(jb.w) != iid && r2 > TINYF) d2 = fminf(d2, r2);
+        }
+    }
+    float4 d = p.iD[i];
+    d.w = d2 * 1.0001f;   // the kernel's own r2 of that pair may round differently
+    const_cast<float4 *>(p.iD)[i] = d;
+}
+
 template <int IPT, bool NN, bool NR, int MINB, bool EPS0>
-__global__ void __launch_bounds__(THREADS, MINB) force_fast_kernel(const ForceArgs p)
+__global__ void __launch_bounds__(THREADS, MINB) force_fast_kernel(const __grid_constant__ ForceArgs p)
 {
     // a pair this close sends its group down the exact path (coincident pairs; with EPS0 also pairs for
     // which r2 + 2^-52 is not r2 in FP32)
     constexpr float R2_EXACT = EPS0 ? 1.4901161193847656e-08f /* 2^-26 */ : TINYF;
-    constexpr bool DUAL = (G6_DUAL != 0) && (IPT >= G6_DUAL);
     static_assert(IPT % 2 == 0, "i-particles are processed in packed pairs");
     static_assert(TILE % GRP == 0 && GRP % (2 * G6_FUNROLL) == 0, "group shape");
     constexpr int NP = IPT / 2;
     constexpr int IB = THREADS * IPT;
+    const float INF = __int_as_float(0x7f800000);
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     ForceSmem &sm = *reinterpret_cast<ForceSmem *>(smem_raw);
@@ -1037,36 +1400,53 @@ __global__ void __launch_bounds__(THREADS, MINB) force_fast_kernel(const ForceAr
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    constexpr uint32_t STAGE_BYTES = 3u * TILE * sizeof(float4);
-    if (tid == 0) {
-        for (int s = 0; s < STAGES && s < ntiles; s++) {
-            size_t off = (size_t)(tile0 + s) * TILE;
-            mbar_expect_tx(&sm.full[s], STAGE_BYTES);
-            bulk_g2s(sm.A[s], p.jA + off, TILE * sizeof(float4), &sm.full[s]);
-            bulk_g2s(sm.B[s], p.jB + off, TILE * sizeof(float4), &sm.full[s]);
-            bulk_g2s(sm.C[s], p.jC + off, TILE * sizeof(float4), &sm.full[s]);
-        }
-    }
+    constexpr uint32_t STAGE_BYTES = 3u * TILE * sizeof(float4) + TBOX * sizeof(float4);
+    auto issue_stage = [&](const int s, const int tile) {
+        const size_t off = (size_t)tile * TILE;
+        mbar_expect_tx(&sm.full[s], STAGE_BYTES);
+        bulk_g2s(sm.A[s], p.jA + off, TILE * sizeof(float4), &sm.full[s]);
+        bulk_g2s(sm.B[s], p.jB + off, TILE * sizeof(float4), &sm.full[s]);
+        bulk_g2s(sm.C[s], p.jC + off, TILE * sizeof(float4), &sm.full[s]);
+        bulk_g2s(sm.G[s], p.jG + (size_t)tile * TBOX, TBOX * sizeof(float4), &sm.full[s]);
+    };
+    if (tid == 0)
+        for (int s = 0; s < STAGES && s < ntiles; s++) issue_stage(s, tile0 + s);
 
-    // ---- register-resident i-pairs: i = block base + 2*tid + {0,1} + q*2*THREADS -------------
+    // ---- register-resident i-pairs: i = block base + IPT*tid + k (consecutive = Morton neighbours) --------
     IPair IP[NP];
-    int iid[IPT];
-    auto i_of = [&](int k) -> int { return blockIdx.y * IB + (tid * 2 + (k & 1)) + (k >> 1) * (2 * THREADS); };
+    int iid[IPT], cgrp[IPT];
+    float closek[IPT];
+    auto i_of = [&](int k) -> int { return blockIdx.y * IB + tid * IPT + k; };
+    float wlo[3] = {INF, INF, INF}, whi[3] = {-INF, -INF, -INF};
+    float closemax = 0.f, nnmax = 0.f;
+    bool several = false;
 #pragma unroll
     for (int q = 0; q < NP; q++) {
         float4 a[2], b[2], c[2];
 #pragma unroll
         for (int h = 0; h < 2; h++) {
-            const int i = i_of(2 * q + h);
+            const int k = 2 * q + h;
+            const int i = i_of(k);
             a[h] = make_float4(0.f, 0.f, 0.f, -1.f);
             b[h] = make_float4(0.f, 0.f, 0.f, __int_as_float(0x80000000));
             c[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+            closek[k] = -1.f;
+            cgrp[k] = -1;
             if (i < p.ni) {
                 a[h] = p.iA[i];
                 b[h] = p.iB[i];
                 c[h] = p.iC[i];
+                const float d2 = p.iD[i].w;
+                const int cf = p.conf[i];
+                closek[k] = (p.ord.kclose > 0.f) ? fminf(p.ord.kclose * d2, p.ord.cap2) : -1.f;
+                closemax = fmaxf(closemax, closek[k]);
+                nnmax = fmaxf(nnmax, d2);
+                several |= (cf == -2);
+                if (cf >= p.slot0) cgrp[k] = (cf - p.slot0) >> 5;
+                wlo[0] = fminf(wlo[0], a[h].x); wlo[1] = fminf(wlo[1], a[h].y); wlo[2] = fminf(wlo[2], a[h].z);
+                whi[0] = fmaxf(whi[0], a[h].x); whi[1] = fmaxf(whi[1], a[h].y); whi[2] = fmaxf(whi[2], a[h].z);
             }
-            iid[2 * q + h] = __float_as_int(b[h].w);
+            iid[k] = __float_as_int(b[h].w);
         }
         IP[q].nxh = pk(-a[0].x, -a[1].x); IP[q].nyh = pk(-a[0].y, -a[1].y); IP[q].nzh = pk(-a[0].z, -a[1].z);
         IP[q].nxl = pk(-b[0].x, -b[1].x); IP[q].nyl = pk(-b[0].y, -b[1].y); IP[q].nzl = pk(-b[0].z, -b[1].z);
@@ -1074,15 +1454,37 @@ __global__ void __launch_bounds__(THREADS, MINB) force_fast_kernel(const ForceAr
         IP[q].id0 = iid[2 * q]; IP[q].id1 = iid[2 * q + 1];
         IP[q].h20 = a[0].w; IP[q].h21 = a[1].w;
     }
+    // the warp's box, largest FP64 radius and largest neighbour bound (warp-uniform from here on)
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            wlo[d] = fminf(wlo[d], __shfl_xor_sync(0xffffffffu, wlo[d], off));
+            whi[d] = fmaxf(whi[d], __shfl_xor_sync(0xffffffffu, whi[d], off));
+        }
+        closemax = fmaxf(closemax, __shfl_xor_sync(0xffffffffu, closemax, off));
+        nnmax = fmaxf(nnmax, __shfl_xor_sync(0xffffffffu, nnmax, off));
+    }
+    const bool always_exact = __any_sync(0xffffffffu, several);
+    const float wsc = fmaxf(fmaxf(fmaxf(fabsf(wlo[0]), fabsf(whi[0])), fmaxf(fabsf(wlo[1]), fabsf(whi[1]))),
+                            fmaxf(fabsf(wlo[2]), fabsf(whi[2])));
+    // a FAR group holds no FP64 pair, no nearest neighbour and no pair the unsoftened shortcut cannot take
+    const float farlim = fmaxf(fmaxf(closemax, NN ? nnmax : 0.f), 1.0e-7f);
+    auto box_gap2 = [&](const float4 lo, const float4 hi) -> float {
+        const float gx = fmaxf(0.f, fmaxf(lo.x - whi[0], wlo[0] - hi.x));
+        const float gy = fmaxf(0.f, fmaxf(lo.y - whi[1], wlo[1] - hi.y));
+        const float gz = fmaxf(0.f, fmaxf(lo.z - whi[2], wlo[2] - hi.z));
+        return gx * gx + gy * gy + gz * gz;
+    };
 
     double D[IPT][7];
     float rmin[IPT], rprev[IPT];   // minimum of r2 over the current group; running minimum (masked rule) before it
-    int jgrp[IPT];                 // first j of the group that last lowered it (local address), -1: none
+    int jgrp[IPT];                 // first j of the group that last lowered it (slot of the window), -1: none
 #pragma unroll
     for (int k = 0; k < IPT; k++) {
 #pragma unroll
         for (int q = 0; q < 7; q++) D[k][q] = 0.0;
-        rmin[k] = rprev[k] = __int_as_float(0x7f800000);
+        rmin[k] = rprev[k] = INF;
         jgrp[k] = -1;
     }
     const float eps2 = p.eps2 + TINYF;   // the reference softens by eps2 + 2^-52 (idata.cc:216)
@@ -1096,29 +1498,68 @@ __global__ void __launch_bounds__(THREADS, MINB) force_fast_kernel(const ForceAr
         const int jtile = (tile0 + t) * TILE;
         int cnt = p.nj - jtile;
         if (cnt > TILE) cnt = TILE;
-        const float4 *tA = sm.A[s], *tB = sm.B[s], *tC = sm.C[s];
+        const float4 *tA = sm.A[s], *tB = sm.B[s], *tC = sm.C[s], *tG = sm.G[s];
 
-        // may this warp meet an equal-id pair in this tile?
-        const int idlo = __float_as_int(tC[0].w), idhi = __float_as_int(tC[1].w);
-        bool hit = false;
+        // whole tile FAR?  (its box is the union of the group boxes)
+        bool tile_far = false;
+        if (!always_exact && cnt == TILE) {
+            const float4 lo = tG[2 * GROUPS_PER_TILE], hi = tG[2 * GROUPS_PER_TILE + 1];
+            const float sc = fmaxf(wsc, lo.w);
+            bool hit = false;
 #pragma unroll
-        for (int k = 0; k < IPT; k++) hit |= (iid[k] >= idlo) & (iid[k] <= idhi);
-        const bool tile_masked = __any_sync(0xffffffffu, hit) || (cnt < TILE);
+            for (int k = 0; k < IPT; k++) hit |= ((cgrp[k] >> 3) == tile0 + t) & (cgrp[k] >= 0);
+            tile_far = (box_gap2(lo, hi) > fmaxf(farlim, p.ord.farc2 * sc * sc)) && !__any_sync(0xffffffffu, hit);
+        }
 
         for (int jj0 = 0; jj0 < cnt; jj0 += GRP) {
-            Acc7P S[NP];
-            bool fast = !tile_masked;
+            int mode = 0;   // 0 FAR, 1 NEAR, 2 CLOSE (FP64)
+            if (!tile_far) {
+                const int gidx = (jtile + jj0) >> 5;
+                const float4 lo = tG[2 * (jj0 >> 5)], hi = tG[2 * (jj0 >> 5) + 1];
+                const float sc = fmaxf(wsc, lo.w);
+                const float gap2 = box_gap2(lo, hi);
+                bool hit = false;
 #pragma unroll
-            for (int k = 0; k < IPT; k++) rmin[k] = __int_as_float(0x7f800000);
-            if (fast) {
-                // DUAL: even and odd j of the group go to separate FP32 partial sums (each spans GRP/2
-                // pairs, which is what bounds the rounding error of a sum dominated by one close pair)
-                Acc7P S1[DUAL ? NP : 1];
+                for (int k = 0; k < IPT; k++) hit |= (cgrp[k] == gidx);
+                if (always_exact || (jj0 + GRP > cnt) || __any_sync(0xffffffffu, hit)) {
+                    mode = 2;
+                } else if (gap2 > fmaxf(farlim, p.ord.farc2 * sc * sc)) {
+                    mode = 0;
+                } else if (gap2 > closemax) {
+                    mode = 1;
+                } else {   // is the box inside the FP64 radius of any particle of the warp?
+                    bool cl = false;
 #pragma unroll
-                for (int q = 0; q < NP; q++) {
-                    S[q] = Acc7P{0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull};
-                    if (DUAL) S1[q] = Acc7P{0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull};
+                    for (int q = 0; q < NP; q++) {
+                        float x0, x1, y0, y1, z0, z1;
+                        upk(IP[q].nxh, x0, x1); upk(IP[q].nyh, y0, y1); upk(IP[q].nzh, z0, z1);   // negated positions
+                        const float ax = fmaxf(0.f, fmaxf(lo.x + x0, -x0 - hi.x)), ay = fmaxf(0.f, fmaxf(lo.y + y0, -y0 - hi.y)),
+                                    az = fmaxf(0.f, fmaxf(lo.z + z0, -z0 - hi.z));
+                        const float bx = fmaxf(0.f, fmaxf(lo.x + x1, -x1 - hi.x)), by = fmaxf(0.f, fmaxf(lo.y + y1, -y1 - hi.y)),
+                                    bz = fmaxf(0.f, fmaxf(lo.z + z1, -z1 - hi.z));
+                        cl |= (ax * ax + ay * ay + az * az <= closek[2 * q]) | (bx * bx + by * by + bz * bz <= closek[2 * q + 1]);
+                    }
+                    mode = __any_sync(0xffffffffu, cl) ? 2 : 1;
                 }
+            }
+            Acc7P S[NP];
+#pragma unroll
+            for (int q = 0; q < NP; q++) S[q] = Acc7P{0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull};
+#pragma unroll
+            for (int k = 0; k < IPT; k++) rmin[k] = INF;
+            if (mode == 0) {
+#pragma unroll FUNROLL
+                for (int u = 0; u < GRP; u += 2) {
+                    const int jj = jj0 + u;
+                    const float4 a0 = tA[jj], c0 = tC[jj];
+                    const float4 a1 = tA[jj + 1], c1 = tC[jj + 1];
+#pragma unroll
+                    for (int q = 0; q < NP; q++) {
+                        interact2_fast<NR, EPS0, true>(a0, a0, c0, IP[q], eps2p, S[q]);
+                        interact2_fast<NR, EPS0, true>(a1, a1, c1, IP[q], eps2p, S[q]);
+                    }
+                }
+            } else if (mode == 1) {
 #pragma unroll FUNROLL
                 for (int u = 0; u < GRP; u += 2) {
                     const int jj = jj0 + u;
@@ -1126,8 +1567,8 @@ __global__ void __launch_bounds__(THREADS, MINB) force_fast_kernel(const ForceAr
                     const float4 a1 = tA[jj + 1], b1 = tB[jj + 1], c1 = tC[jj + 1];
 #pragma unroll
                     for (int q = 0; q < NP; q++) {
-                        const u64 ra = interact2_fast<NR, EPS0>(a0, b0, c0, IP[q], eps2p, S[q]);
-                        const u64 rb = interact2_fast<NR, EPS0>(a1, b1, c1, IP[q], eps2p, DUAL ? S1[q] : S[q]);
+                        const u64 ra = interact2_fast<NR, EPS0, false>(a0, b0, c0, IP[q], eps2p, S[q]);
+                        const u64 rb = interact2_fast<NR, EPS0, false>(a1, b1, c1, IP[q], eps2p, S[q]);
                         float ra0, ra1, rb0, rb1;
                         upk(ra, ra0, ra1);
                         upk(rb, rb0, rb1);
@@ -1135,50 +1576,40 @@ __global__ void __launch_bounds__(THREADS, MINB) force_fast_kernel(const ForceAr
                         rmin[2 * q + 1] = min3f(rmin[2 * q + 1], ra1, rb1);
                     }
                 }
-                if (DUAL) {
-#pragma unroll
-                    for (int q = 0; q < NP; q++) {
-                        S[q].ax = add2(S[q].ax, S1[q].ax); S[q].ay = add2(S[q].ay, S1[q].ay);
-                        S[q].az = add2(S[q].az, S1[q].az); S[q].jx = add2(S[q].jx, S1[q].jx);
-                        S[q].jy = add2(S[q].jy, S1[q].jy); S[q].jz = add2(S[q].jz, S1[q].jz);
-                        S[q].pot = add2(S[q].pot, S1[q].pot);
-                    }
-                }
                 bool bad = false;
 #pragma unroll
                 for (int k = 0; k < IPT; k++) bad |= !(rmin[k] > R2_EXACT);
-                if (__any_sync(0xffffffffu, bad)) {   // a pair too close for the fast path: redo the group exactly
-                    fast = false;
+                if (__any_sync(0xffffffffu, bad)) mode = 2;   // a pair too close for the mask-free path
+            }
+            if (mode == 2) {
+                const int n = (cnt - jj0 < GRP) ? cnt - jj0 : GRP;
 #pragma unroll
-                    for (int k = 0; k < IPT; k++) rmin[k] = __int_as_float(0x7f800000);
+                for (int q = 0; q < NP; q++) {
+                    F64Group o;
+                    fp64_group(&o, &p, jtile + jj0, n, tA + jj0, tB + jj0, tC + jj0, IP[q], i_of(2 * q));
+#pragma unroll
+                    for (int c = 0; c < 7; c++) {
+                        D[2 * q][c] += o.v[0][c];
+                        D[2 * q + 1][c] += o.v[1][c];
+                    }
+                    rmin[2 * q] = o.rmin[0];
+                    rmin[2 * q + 1] = o.rmin[1];
+                }
+            } else {
+                // the mask-free pair function accumulates -acc, -jerk
+#pragma unroll
+                for (int q = 0; q < NP; q++) {
+                    float lo, hi;
+                    upk(S[q].ax, lo, hi); D[2 * q][0] -= (double)lo; D[2 * q + 1][0] -= (double)hi;
+                    upk(S[q].ay, lo, hi); D[2 * q][1] -= (double)lo; D[2 * q + 1][1] -= (double)hi;
+                    upk(S[q].az, lo, hi); D[2 * q][2] -= (double)lo; D[2 * q + 1][2] -= (double)hi;
+                    upk(S[q].jx, lo, hi); D[2 * q][3] -= (double)lo; D[2 * q + 1][3] -= (double)hi;
+                    upk(S[q].jy, lo, hi); D[2 * q][4] -= (double)lo; D[2 * q + 1][4] -= (double)hi;
+                    upk(S[q].jz, lo, hi); D[2 * q][5] -= (double)lo; D[2 * q + 1][5] -= (double)hi;
+                    upk(S[q].pot, lo, hi); D[2 * q][6] += (double)lo; D[2 * q + 1][6] += (double)hi;
                 }
             }
-            if (!fast) {
-#pragma unroll
-                for (int q = 0; q < NP; q++) S[q] = Acc7P{0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull};
-                const int jend = (jj0 + GRP < cnt) ? jj0 + GRP : cnt;
-                for (int jj = jj0; jj < jend; jj++) {
-                    const float4 a = tA[jj], b = tB[jj], c = tC[jj];
-                    int unused0 = 0, unused1 = 0;
-#pragma unroll
-                    for (int q = 0; q < NP; q++)
-                        interact2<true, false, NR, false>(a, b, c, 0, IP[q], eps2p, S[q], rmin[2 * q], unused0,
-                                                          rmin[2 * q + 1], unused1, 0, p);
-                }
-            }
-            const double sg = fast ? -1.0 : 1.0;   // the mask-free pair function accumulates -acc, -jerk
-#pragma unroll
-            for (int q = 0; q < NP; q++) {
-                float lo, hi;
-                upk(S[q].ax, lo, hi); D[2 * q][0] += sg * (double)lo; D[2 * q + 1][0] += sg * (double)hi;
-                upk(S[q].ay, lo, hi); D[2 * q][1] += sg * (double)lo; D[2 * q + 1][1] += sg * (double)hi;
-                upk(S[q].az, lo, hi); D[2 * q][2] += sg * (double)lo; D[2 * q + 1][2] += sg * (double)hi;
-                upk(S[q].jx, lo, hi); D[2 * q][3] += sg * (double)lo; D[2 * q + 1][3] += sg * (double)hi;
-                upk(S[q].jy, lo, hi); D[2 * q][4] += sg * (double)lo; D[2 * q + 1][4] += sg * (double)hi;
-                upk(S[q].jz, lo, hi); D[2 * q][5] += sg * (double)lo; D[2 * q + 1][5] += sg * (double)hi;
-                upk(S[q].pot, lo, hi); D[2 * q][6] += (double)lo; D[2 * q + 1][6] += (double)hi;
-            }
-            if (NN) {
+            if (NN && mode != 0) {
 #pragma unroll
                 for (int k = 0; k < IPT; k++) {
                     if (rmin[k] < rprev[k]) {   // strict: the first group that reaches the minimum keeps it
@@ -1190,13 +1621,7 @@ __global__ void __launch_bounds__(THREADS, MINB) force_fast_kernel(const ForceAr
         }
 
         __syncthreads();  // everyone is done with stage s
-        if (tid == 0 && t + STAGES < ntiles) {
-            size_t off = (size_t)(tile0 + t + STAGES) * TILE;
-            mbar_expect_tx(&sm.full[s], STAGE_BYTES);
-            bulk_g2s(sm.A[s], p.jA + off, TILE * sizeof(float4), &sm.full[s]);
-            bulk_g2s(sm.B[s], p.jB + off, TILE * sizeof(float4), &sm.full[s]);
-            bulk_g2s(sm.C[s], p.jC + off, TILE * sizeof(float4), &sm.full[s]);
-        }
+        if (tid == 0 && t + STAGES < ntiles) issue_stage(s, tile0 + t + STAGES);
     }
 
     // ---- nearest neighbour: re-scan the one group that holds the minimum ---------------------
@@ -1219,7 +1644,7 @@ __global__ void __launch_bounds__(THREADS, MINB) force_fast_kernel(const ForceAr
                 }
             }
         }
-        key[k] = (jm >= 0) ? make_key(rprev[k], jm + p.j_offset) : KEY_NONE;
+        key[k] = (jm >= 0) ? make_key(rprev[k], jm) : KEY_NONE;
     }
 
     // ---- totals -> global (final or per-split partial) -----------------------------------
@@ -1293,9 +1718,10 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const ForceArgs p,
     signal_done(p);
 }
 
-// After a min-reduction of keys over ranks (each rank holds a j-shard).
+// After a min-reduction of keys over ranks (each rank holds a j-shard): the id of the winner if this rank
+// owns it (keys carry the reported address = local address + j_offset).
 __global__ void resolve_nn_kernel(int ni, const u64 *__restrict__ key, int rank, int j_offset, int nj_local,
-                                  const float4 *__restrict__ jB, int *nnid)
+                                  const int *__restrict__ slot_of, const float4 *__restrict__ jB, int *nnid)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= ni) return;
@@ -1305,9 +1731,106 @@ __global__ void resolve_nn_kernel(int ni, const u64 *__restrict__ key, int rank,
         id = (rank == 0) ? -1 : 0;
     } else {
         int a = (int)(unsigned)(k & 0xffffffffu) - j_offset;
-        if (a >= 0 && a < nj_local) id = __float_as_int(jB[a].w);
+        if (a >= 0 && a < nj_local) id = __float_as_int(jB[slot_of[a]].w);
     }
     nnid[i] = id;
+}
+
+// ---------------------------------------------------------------------------
+// j-memory order (host: rebuild_order): bounding box, Morton keys, permutation, id table, neighbour bounds.
+// ---------------------------------------------------------------------------
+// box[0..2] = min, box[3..5] = max of the positions of the massive particles with address < nj (ordered ints)
+__global__ void __launch_bounds__(256) order_box_kernel(const int n, const int nj, const JState s, const int *addr_of,
+                                                        int *box)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool use = (j < n) && (addr_of[j] < nj) && (s.q[6][j].y > (double)TINYF);
+    float x = 0.f, y = 0.f, z = 0.f;
+    if (use) {
+        x = (float)s.q[0][j].x;
+        y = (float)s.q[0][j].y;
+        z = (float)s.q[1][j].x;
+    }
+    const int big = 0x7f7fffff, small = f2ord(-3.0e38f);
+    int v[6] = {use ? f2ord(x) : big, use ? f2ord(y) : big, use ? f2ord(z) : big,
+                use ? f2ord(x) : small, use ? f2ord(y) : small, use ? f2ord(z) : small};
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        v[d] = __reduce_min_sync(0xffffffffu, v[d]);
+        v[3 + d] = __reduce_max_sync(0xffffffffu, v[3 + d]);
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            atomicMin(&box[d], v[d]);
+            atomicMax(&box[3 + d], v[3 + d]);
+        }
+    }
+}
+// sort keys: Morton key of the position (relative to x0) for massive particles of the prefix [0, nj);
+// massless ones go to the end of the prefix, addresses >= nj behind it in address order
+__global__ void __launch_bounds__(256) order_key_kernel(const int n, const int nj, const JState s, const int *addr_of,
+                                                        const OrderInfo o, unsigned *key, int *val)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const int a = addr_of[j];
+    unsigned k;
+    if (a >= nj) {
+        k = 0x80000000u | (unsigned)a;
+    } else if (!(s.q[6][j].y > (double)TINYF)) {
+        k = 0x7fffffffu;
+    } else {
+        k = morton30((float)(s.q[0][j].x - s.x0[0]), (float)(s.q[0][j].y - s.x0[1]), (float)(s.q[1][j].x - s.x0[2]), o.blo,
+                     o.binv);
+    }
+    key[j] = k;
+    val[j] = j;
+}
+// new slot j takes what old slot perm[j] held
+__global__ void __launch_bounds__(256) order_permute_kernel(const int n, const int *__restrict__ perm, const JState from,
+                                                            const int *__restrict__ addr_from, JState to, int *addr_to,
+                                                            int *slot_of)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const int o = perm[j];
+#pragma unroll
+    for (int k = 0; k < 7; k++) to.q[k][j] = from.q[k][o];
+    to.ia[j] = from.ia[o];
+    to.near2[j] = from.near2[o];
+    const int a = addr_from[o];
+    addr_to[j] = a;
+    slot_of[a] = j;
+}
+// upper bound of every particle's nearest-neighbour distance from its 2W Morton neighbours (state positions)
+__global__ void __launch_bounds__(256) order_near_kernel(const int n, const JState s, const int W)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    float d2 = __int_as_float(0x7f800000);
+    if (s.q[6][j].y > (double)TINYF) {
+        const double x = s.q[0][j].x, y = s.q[0][j].y, z = s.q[1][j].x;
+        const int id = s.ia[j].x;
+        const int lo = max(0, j - W), hi = min(n, j + W + 1);
+        for (int k = lo; k < hi; k++) {
+            if (k == j || s.ia[k].x == id || !(s.q[6][k].y > (double)TINYF)) continue;
+            const double dx = s.q[0][k].x - x, dy = s.q[0][k].y - y, dz = s.q[1][k].x - z;
+            const float r2 = (float)(dx * dx + dy * dy + dz * dz);
+            if (r2 > TINYF) d2 = fminf(d2, r2);
+        }
+    }
+    s.near2[j] = d2;
+}
+// Morton keys of an i-set (device-resident callers), for the sort that precedes pack_i_kernel
+__global__ void __launch_bounds__(256) i_key_kernel(const int ni, const double *__restrict__ xi, const JState s,
+                                                    const OrderInfo o, unsigned *key, int *val)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ni) return;
+    key[i] = morton30((float)(xi[3 * (size_t)i] - s.x0[0]), (float)(xi[3 * (size_t)i + 1] - s.x0[1]),
+                      (float)(xi[3 * (size_t)i + 2] - s.x0[2]), o.blo, o.binv);
+    val[i] = i;
 }
 
 // ---------------------------------------------------------------------------
@@ -1321,32 +1844,23 @@ __global__ void resolve_nn_kernel(int ni, const u64 *__restrict__ key, int rank,
 
 __device__ __forceinline__ void hermite_gather_one(const HermiteArgs &h, const int i)
 {
-    const int a = h.ilist[i];
+    const int a = h.slot_of[h.ilist[i]];
     const JState &s = h.js;
-    const double2 q0 = s.q[0][a], q1 = s.q[1][a], q2 = s.q[2][a], q3 = s.q[3][a], q4 = s.q[4][a], q5 = s.q[5][a],
-                  q6 = s.q[6][a];
-    const double x = q0.x, y = q0.y, z = q1.x, tj = q1.y, vx = q2.x, vy = q2.y, vz = q3.x;
-    const double ax = q3.y, ay = q4.x, az = q4.y, jx = q5.x, jy = q5.y, jz = q6.x;
-    const int id = __double2hiint(q6.y);
-    const double dt = h.tnext - tj;
-    double px = x, py = y, pz = z, qx = vx, qy = vy, qz = vz;
-    if (dt != 0.0) {  // idata.cc:353-361
-        px = x + dt * (vx + 0.5 * dt * (ax + dt * jx / 3));
-        py = y + dt * (vy + 0.5 * dt * (ay + dt * jy / 3));
-        pz = z + dt * (vz + 0.5 * dt * (az + dt * jz / 3));
-        qx = vx + dt * (ax + 0.5 * dt * jx);
-        qy = vy + dt * (ay + 0.5 * dt * jy);
-        qz = vz + dt * (az + 0.5 * dt * jz);
-    }
+    const PredJ pj = predict_slot(s, a, h.tnext);   // idata.cc:353-361 is the same polynomial as jdata.cc:739-746
+    const int id = s.ia[a].x;
+    const double px = pj.x, py = pj.y, pz = pj.z, qx = pj.vx, qy = pj.vy, qz = pj.vz;
     double *pr = h.pred + (size_t)i * 6;
     pr[0] = px; pr[1] = py; pr[2] = pz; pr[3] = qx; pr[4] = qy; pr[5] = qz;
     h.ilist_d[i] = a;
     h.olddt_d[i] = (h.mode == 0) ? h.old_dt[i] : 0.0;
-    const float xh = (float)px, yh = (float)py, zh = (float)pz;
+    const double rx = px - s.x0[0], ry = py - s.x0[1], rz = pz - s.x0[2];
+    const float xh = (float)rx, yh = (float)ry, zh = (float)rz;
+    const float vxh = (float)qx, vyh = (float)qy, vzh = (float)qz;
     h.iA[i] = make_float4(xh, yh, zh, 0.f);
-    h.iB[i] = make_float4((float)(px - (double)xh), (float)(py - (double)yh), (float)(pz - (double)zh),
+    h.iB[i] = make_float4((float)(rx - (double)xh), (float)(ry - (double)yh), (float)(rz - (double)zh),
                           __int_as_float(id));
-    h.iC[i] = make_float4((float)qx, (float)qy, (float)qz, 0.f);
+    h.iC[i] = make_float4(vxh, vyh, vzh, 0.f);
+    h.iD[i] = make_float4((float)(qx - (double)vxh), (float)(qy - (double)vyh), (float)(qz - (double)vzh), 0.f);
 }
 
 // Corrector (or initialisation) of active particle i given its new force f[7] and neighbour id.
@@ -1447,9 +1961,8 @@ __global__ void __launch_bounds__(256) hermite_correct_kernel(const HermiteArgs 
 __global__ void __launch_bounds__(TILE) hermite_predict_gather_kernel(const int ntiles, const int n, const double ti,
                                                                       const HermiteArgs h)
 {
-    __shared__ int sh_lo[TILE / 32], sh_hi[TILE / 32];
     if ((int)blockIdx.x < ntiles) {
-        predict_tile(blockIdx.x, n, ti, h.js, sh_lo, sh_hi);
+        predict_tile(blockIdx.x, n, ti, h.js);
         return;
     }
     const int i = (blockIdx.x - ntiles) * TILE + threadIdx.x;
@@ -1488,9 +2001,11 @@ __global__ void peer_flag_kernel(const PeerSlots ps, const unsigned long long se
 }
 
 // grid <= resident CTAs (the host sizes it): every CTA waits, then takes a grid-stride share of i
+// host_flag != NULL (single CTA): the totals go to mapped host memory and the flag announces them.
 __global__ void __launch_bounds__(256) peer_combine_kernel(const PeerSlots ps, const unsigned long long seq, const int ni,
                                                           double *out_sum, u64 *out_key, int *out_nnid,
-                                                          unsigned int *error_word)
+                                                          unsigned int *error_word, unsigned long long *host_flag,
+                                                          const unsigned long long flag_seq)
 {
     __shared__ int ok;
     if (threadIdx.x == 0) {
@@ -1528,6 +2043,11 @@ __global__ void __launch_bounds__(256) peer_combine_kernel(const PeerSlots ps, c
         for (int q = 0; q < 7; q++) out_sum[(size_t)i * 7 + q] = tot[q];
         out_key[i] = kk;
         out_nnid[i] = id;
+    }
+    if (host_flag) {   // gridDim.x == 1
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) *reinterpret_cast<volatile unsigned long long *>(host_flag) = flag_seq;
     }
 }
 

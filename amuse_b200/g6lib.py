@@ -31,6 +31,7 @@ G6_SYMBOLS = [
     "g6x_read_predicted", "g6x_time_predictor", "g6x_set_variant", "g6x_fp32_peak",
     "g6x_peer_handle_bytes", "g6x_peer_alloc", "g6x_peer_attach", "g6x_peer_detach", "g6x_peer_error",
     "g6x_calc_device_allreduce", "g6x_hermite_init", "g6x_hermite_step", "g6x_hermite_evolve", "g6x_hermite_get_state", "g6x_hermite_set_shard", "g6x_latency_probe",
+    "g6x_set_close_factor", "g6x_order_rebuilds", "g6x_device_count_open",
 ]
 
 _dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
@@ -63,6 +64,8 @@ def load():
     L.g6_get_neighbour_list_.argtypes = [_pi, _pi, _pi, _pi, _ip]
     L.g6x_set_stream.argtypes = [C.c_void_p, C.c_int]
     L.g6x_set_refine.argtypes = [C.c_int]
+    L.g6x_set_close_factor.argtypes = [C.c_double, C.c_double]
+    L.g6x_order_rebuilds.restype = C.c_longlong
     L.g6x_set_j_offset.argtypes = [C.c_int]
     L.g6x_set_j_particles.argtypes = [C.c_int, C.c_void_p, C.c_int, _ip, C.c_void_p, _dp, C.c_void_p,
                                       C.c_void_p, _dp, _dp]
@@ -202,6 +205,10 @@ class G6:
     def set_variant(self, v):
         if self.L.g6x_set_variant(int(v)) != 0:
             raise ValueError("unknown force-kernel variant %r" % (v,))
+
+    def set_close_factor(self, k_close=-1.0, far_factor=-1.0):
+        """FP64 radius factor / FAR-block factor of the pair classification (negative: unchanged)."""
+        self.L.g6x_set_close_factor(float(k_close), float(far_factor))
 
     def launch_count(self):
         return int(self.L.g6x_launch_count())

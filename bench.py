@@ -303,7 +303,7 @@ def run_b200(a):
     ffma2 = L.g6x_fp32_peak(1)
     # predictor: HBM-bound kernel, 112 B read + 48 B written per j
     pred_ms = L.g6x_time_predictor(njl, 20)
-    pred_gbs = 160.0 * njl / (pred_ms * 1e-3) / 1e9 if pred_ms > 0 else None
+    pred_gbs = 185.0 * njl / (pred_ms * 1e-3) / 1e9 if pred_ms > 0 else None
 
     # j-update path (g6x_set_j_particles: host staging of 128 B records -> pinned batches -> H2D -> scatter_kernel):
     # reload this rank's whole j-shard and make it visible to the next force call
@@ -395,7 +395,7 @@ def run_b200(a):
                          "kernel_share_of_step": kernel_share,
                          "measured_ffma_tflops": ffma, "measured_ffma2_tflops": ffma2,
                          "frac_of_measured_ffma": achieved / max(ffma, ffma2, 1e-9)},
-            "predictor": {"bound": "hbm", "achieved": pred_gbs, "unit": "GB/s", "bytes_per_j": 160,
+            "predictor": {"bound": "hbm", "achieved": pred_gbs, "unit": "GB/s", "bytes_per_j": 185,
                           "ms_per_launch": pred_ms},
             "j_update": j_update,
             "e2e": e2e, "cpu_baseline": cpu, "gpu_launches": int(launches), "clocks": clocks,

@@ -145,6 +145,17 @@ int g6x_set_stream(void *cuda_stream, int external);
 /* 1 (default): one Newton step on the reciprocal square root (per-pair error at
  * the FP32 rounding floor); 0: raw MUFU.RSQ (2^-22.9), ~10 % faster. */
 int g6x_set_refine(int on);
+/* Accuracy / speed parameters of the pair classification (defaults: G6_B200_KCLOSE = 16, G6_B200_FARC = 0.125):
+ * k_close: pairs closer than sqrt(k_close) x (the i-particle's nearest-neighbour distance) are evaluated
+ * in FP64 with the reference's expression tree (0 switches that off: plain FP32 pair arithmetic);
+ * far_factor: (warp of i) x (group of j) blocks whose bounding boxes are further apart than far_factor x
+ * (largest |coordinate| relative to the library's origin) take position differences from the hi parts of the
+ * double-single coordinates alone.  A negative value leaves that parameter unchanged. */
+int g6x_set_close_factor(double k_close, double far_factor);
+/* How often the j-memory has been re-ordered (Morton sort + id table) since g6_open_. */
+long long g6x_order_rebuilds(void);
+/* Devices g6_open_ opened (G6_B200_DEVICES; 0 when closed). */
+int g6x_device_count_open(void);
 /* This process owns j-addresses whose GLOBAL address is local + offset (used
  * when j is sharded over ranks; the offset is packed in the nearest-neighbour
  * keys so a min-reduction over ranks is meaningful). */

@@ -3,34 +3,20 @@
 Per-particle vector-norm relative errors against ph4's FP64 CPU loop:
     e_acc = |a - a_ref| / |a_ref|,  e_jerk likewise,  e_pot = |p - p_ref| / |p_ref|.
 
-Tolerances written here and asserted by every parity test:
-  * acc, pot : max over all particles <= 1e-6  (the north-star bound).  When the oracle provides
-               the condition scale S_i = sum_j |a_ij| (``scales=True``), a particle whose force is a
-               cancelling sum (kappa_i = S_i/|a_i| > 8: field points inside the cluster, e.g. the
-               random probes of test_ragged_sizes with kappa up to 41, and the ~1 % of members that sit
-               near the cluster centre, where the smooth field vanishes) is held to
-               |da_i| <= 1e-6 * S_i/4 = 4.2 * 2^-24 * S_i instead: FP32 pair arithmetic has a per-pair
-               error of ~1.5e-7 = 2.5 * 2^-24 rms (rounding of dx and r2, tools/emulate_kernel.py), which
-               a cancellation factor kappa amplifies in ANY summation order or precision of the sums;
-               when two close neighbours dominate S_i the pair errors do not average down, and
-               1.3e-7 * S_i is observed (test_block_step_sequence..., kappa 15).  Particles with
-               kappa <= 8 (typical member: kappa ~ 1.5) are always held to the plain 1e-6.
-  * jerk     : 99th percentile <= 1e-6; max <= 1e-5; and, when the oracle provides the condition
-               scale S_i = sum_j |jerk_ij|, every particle satisfies |dj_i| <= 1e-6 * S_i (same for acc).
-    Why jerk differs: the library is mandated to do FP32 pair arithmetic on double-single
-    positions.  jerk_i is a sum of terms of random sign, so for a few particles per thousand the
-    total is ~10x smaller than the terms; the 2^-24 rounding of dx alone (everything downstream in
-    FP64) already gives max e_jerk ~ 1e-6..2e-6 at N = 1k (tools/fp32_floor_emulation.py, DESIGN.md
-    "accuracy").  1e-5 is the tolerance the reference's own GPU-vs-CPU test uses
-    (src/amuse_ph4/tests/test_ph4.py:848-872).
+Tolerance written here and asserted by every parity test: the north-star's 1e-6 on the per-particle MAXIMUM of
+all three, for every particle -- field probes inside the cluster and members next to the cluster centre, whose
+acc and jerk are cancelling sums, included.  (Round 1 held jerk to 1e-5 and gave cancelling acc sums a conditioned
+bound; since round 2 the library evaluates every pair closer than sqrt(K) x the i-particle's nearest-neighbour
+distance in FP64 with the reference's expression tree, K = 16 by default, so the pairs that dominate a cancelling
+sum no longer carry the 2^-24 rounding of dx: tools/emulate_v2.py, DESIGN.md "Accuracy".)
+When the oracle provides the condition scales S_i = sum_j |a_ij| and sum_j |jerk_ij|, the backward-stable bound
+|d_i| <= 1e-6 * S_i is asserted as well (it is the weaker statement for every particle).
 """
 import numpy as np
 
-TOL = 1e-6          # acc / pot max, jerk 99th percentile
-TOL_JERK_MAX = 1e-5
+TOL = 1e-6          # acc / jerk / pot: per-particle maximum
+TOL_JERK_MAX = 1e-6
 TOL_JERK_SCALED = 1e-6
-KAPPA_WELL_CONDITIONED = 8.0   # above this, the bound is relative to S_i / CANCELLING_SCALE
-CANCELLING_SCALE = 4.0
 
 
 def rel_vec_err(a, b):
@@ -46,20 +32,9 @@ def check_forces(got, ref, tol=TOL, what=""):
     ea = rel_vec_err(got["acc"], ref["acc"])
     ej = rel_vec_err(got["jerk"], ref["jerk"])
     ep = rel_err(got["pot"], ref["pot"])
-    if "sacc" in ref:
-        na = np.maximum(np.linalg.norm(ref["acc"], axis=1), 1e-300)
-        kappa = ref["sacc"] / na
-        # |da| / |a| for well-conditioned sums, |da| / (S/4) for cancelling ones
-        ea_c = np.where(kappa > KAPPA_WELL_CONDITIONED, ea / (kappa / CANCELLING_SCALE), ea)
-        assert ea_c.max() <= tol, "%s acc rel err %.3e (conditioned %.3e, kappa %.1f)" % (
-            what, ea.max(), ea_c.max(), kappa[np.argmax(ea_c)])
-    else:
-        assert ea.max() <= tol, "%s acc rel err %.3e" % (what, ea.max())
+    assert ea.max() <= tol, "%s acc rel err %.3e" % (what, ea.max())
     assert ep.max() <= tol, "%s pot rel err %.3e" % (what, ep.max())
     assert ej.max() <= TOL_JERK_MAX, "%s jerk rel err max %.3e" % (what, ej.max())
-    if len(ej) >= 200:
-        p99 = np.percentile(ej, 99)
-        assert p99 <= tol, "%s jerk rel err p99 %.3e" % (what, p99)
     if "sjerk" in ref:
         sc = np.linalg.norm(got["jerk"] - ref["jerk"], axis=1) / ref["sjerk"]
         assert sc.max() <= TOL_JERK_SCALED, "%s jerk err / sum|terms| %.3e" % (what, sc.max())
