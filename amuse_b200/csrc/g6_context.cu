@@ -23,6 +23,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <limits>
 #include <vector>
 
 using namespace g6b;
@@ -97,11 +98,12 @@ struct Context {
     void *d_sort_tmp = nullptr;
     size_t sort_tmp_bytes = 0;
     int sort_cap = 0;
-    int *d_box = nullptr, *h_box = nullptr;   // 6 ordered ints
+    int *d_box = nullptr, *h_box = nullptr;   // 6 ordered ints + (at byte 32) 4 doubles: sum of positions, count
     u64 *d_hash = nullptr;
     unsigned hash_size = 0;
     OrderInfo ord{};
     bool order_valid = false;
+    bool order_tiny = false;           // <= 64 j: all pairs go to FP64
     int order_nj = -1;
     bool ids_dirty = false;
     long long updates_since_order = 0, updates_since_force = 0;
@@ -109,6 +111,14 @@ struct Context {
     float kclose = 16.f;               // G6_B200_KCLOSE
     float farc = 0.125f;               // G6_B200_FARC
     int near_w = 32;                   // Morton window (each side) of the neighbour-bound scans
+    unsigned long long *d_stats = nullptr;   // block-class counters (-DG6_STATS builds)
+    // FP64 pairs: global list of the speculative kernel + per-particle results (see ForceArgs)
+    int2 *d_wl = nullptr;
+    unsigned int *d_wl_count = nullptr;
+    size_t wl_cap = 0;
+    double *d_corr = nullptr;
+    size_t corr_cap = 0;
+    int wl_per_i = 512;                // G6_B200_WL_PER_I: list entries reserved per i-particle of a launch
     double ti = 0.0;
     double predicted_ti = 0.0;
     int predicted_nj = -1;  // prefix predicted at predicted_ti (-1: none)
@@ -474,14 +484,17 @@ void rebuild_order(int nj)
     G.ord = OrderInfo{};
     G.ord.kclose = G.kclose;
     G.ord.farc2 = G.farc * G.farc;
+    G.order_tiny = false;
     if (n <= 0 || nj <= 0) return;
     G.order_rebuilds++;
     cudaStream_t st = G.stream;
     const int blocks = (n + 255) / 256;
     if (!G.d_box) {
-        dev_alloc(G.d_box, 8);
-        host_alloc(G.h_box, 8);
+        dev_alloc(G.d_box, 16);
+        host_alloc(G.h_box, 16);
     }
+    double *h_cen = reinterpret_cast<double *>(G.h_box + 8), *d_cen = reinterpret_cast<double *>(G.d_box + 8);
+    for (int d = 0; d < 4; d++) h_cen[d] = 0.0;
     union { int i; float f; } cv;
     auto ord_i = [&](float f) { cv.f = f; return cv.i >= 0 ? cv.i : cv.i ^ 0x7fffffff; };
     auto ord_f = [&](int i) { cv.i = i >= 0 ? i : i ^ 0x7fffffff; return cv.f; };
@@ -489,17 +502,20 @@ void rebuild_order(int nj)
         G.h_box[d] = 0x7f7fffff;
         G.h_box[3 + d] = ord_i(-3.0e38f);
     }
-    CK(cudaMemcpyAsync(G.d_box, G.h_box, 6 * sizeof(int), cudaMemcpyHostToDevice, st));
-    order_box_kernel<<<blocks, 256, 0, st>>>(n, nj, G.js, G.addr_of, G.d_box);
+    CK(cudaMemcpyAsync(G.d_box, G.h_box, 16 * sizeof(int), cudaMemcpyHostToDevice, st));
+    order_box_kernel<<<blocks, 256, 0, st>>>(n, nj, G.js, G.addr_of, G.d_box, d_cen);
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(G.h_box, G.d_box, 6 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(G.h_box, G.d_box, 16 * sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     double lo[3], hi[3], diag2 = 0.0;
     for (int d = 0; d < 3; d++) {
         lo[d] = ord_f(G.h_box[d]);
         hi[d] = ord_f(G.h_box[3 + d]);
         if (!(hi[d] >= lo[d])) lo[d] = hi[d] = 0.0;   // no massive particle
-        G.js.x0[d] = 0.5 * (lo[d] + hi[d]);
+        // origin: the mean position (not the box centre, which a single escaper drags away from the cluster);
+        // in the multi-device mode all devices share device 0's origin, the i-block is packed once
+        G.js.x0[d] = (g_cur != &g_ctx[0] && g_ctx[0].order_valid) ? g_ctx[0].js.x0[d]
+                                                                   : (h_cen[3] > 0.0 ? h_cen[d] / h_cen[3] : 0.0);
         const double ext = hi[d] - lo[d];
         diag2 += ext * ext;
         G.ord.blo[d] = (float)(lo[d] - G.js.x0[d]);
@@ -507,6 +523,12 @@ void rebuild_order(int nj)
     }
     for (int d = 0; d < 3; d++) G.js2.x0[d] = G.js.x0[d];
     G.ord.cap2 = (float)(diag2 / 64.0);   // (diagonal / 8)^2
+    // a handful of j (two-body and few-body tests, BHTree's shortest lists): every pair in FP64
+    G.order_tiny = std::min(nj, n) <= 64;
+    if (G.order_tiny && G.kclose > 0.f) {
+        G.ord.kclose = 1.0e30f;
+        G.ord.cap2 = std::numeric_limits<float>::infinity();
+    }
     // keys, sort, permutation
     order_key_kernel<<<blocks, 256, 0, st>>>(n, nj, G.js, G.addr_of, G.ord, G.d_keys_tmp, G.d_vals_tmp);
     CK(cudaGetLastError());
@@ -519,7 +541,8 @@ void rebuild_order(int nj)
         G.sort_tmp_bytes = need;
     }
     CK(cub::DeviceRadixSort::SortPairs(G.d_sort_tmp, need, G.d_keys_tmp, G.d_keys, G.d_vals_tmp, G.d_vals, n, 0, 32, st));
-    order_permute_kernel<<<blocks, 256, 0, st>>>(n, G.d_vals, G.js, G.addr_of, G.js2, G.addr_of2, G.js.slot_of);
+    order_permute_kernel<<<(G.capacity + 255) / 256, 256, 0, st>>>(n, G.capacity, G.d_vals, G.js, G.addr_of, G.js2,
+                                                                   G.addr_of2, G.js.slot_of);
     CK(cudaGetLastError());
     for (int k = 0; k < 7; k++) std::swap(G.js.q[k], G.js2.q[k]);
     std::swap(G.js.ia, G.js2.ia);
@@ -561,6 +584,32 @@ bool order_stale(int nj)
                        G.updates_since_order >= 4LL * std::max(nj, 1);
     G.updates_since_force = 0;
     return stale;
+}
+
+// per-particle FP64 pair results for launches of up to ni particles (zero between launches: whoever writes a
+// particle's outputs clears its entry); with_list: also the global pair list of the speculative kernel
+void ensure_close_buffers(size_t ni, bool with_list)
+{
+    if (ni > G.corr_cap) {
+        CK(cudaStreamSynchronize(G.stream));
+        dev_free(G.d_corr);
+        const size_t cap = std::max<size_t>(ni, std::max<size_t>(G.npipes, 2 * G.corr_cap));
+        dev_alloc(G.d_corr, cap * 7);
+        CK(cudaMemsetAsync(G.d_corr, 0, cap * 7 * sizeof(double), G.stream));
+        G.corr_cap = cap;
+    }
+    if (!with_list) return;
+    if (!G.d_wl_count) {
+        dev_alloc(G.d_wl_count, 1);
+        CK(cudaMemsetAsync(G.d_wl_count, 0, sizeof(unsigned int), G.stream));
+    }
+    const size_t want = std::min<size_t>((size_t)G.wl_per_i * ni, (size_t)1 << 26);
+    if (want > G.wl_cap) {
+        CK(cudaStreamSynchronize(G.stream));
+        dev_free(G.d_wl);
+        dev_alloc(G.d_wl, want);
+        G.wl_cap = want;
+    }
 }
 
 void ensure_partials(size_t records)
@@ -807,6 +856,7 @@ void launch_force(int nj, int ni, const IBlock &ib, float eps2, bool nn, bool li
     a.iA = ib.A; a.iB = ib.B; a.iC = ib.C; a.iD = ib.D;
     a.conf = ib.conf;
     a.iperm = ib.iperm;
+    a.stats = G.d_stats;
     a.ni = ni; a.nj = nj;
     a.tiles_per_split = tps; a.nsplit = nsplit;
     a.ni_pad = ni;
@@ -817,10 +867,23 @@ void launch_force(int nj, int ni, const IBlock &ib, float eps2, bool nn, bool li
     // many splits of few i-blocks: sum the partials with a kernel of its own (one warp per i, spread
     // over the SMs) instead of the last CTA -- except for the 4-particle shape, whose last CTA puts
     // 32 lanes on each i
-    const bool defer = (nsplit > 32) && (n_iblocks * 8 <= slots) && (vi.ib > 4) && !herm;
+    // the speculative kernel always stops at the partials when FP64 pairs are in use: they are evaluated by
+    // close_pairs_kernel before reduce_partials_kernel adds everything up
+    const bool fastv = (v == V_F2 || v == V_F4);
+    const bool use_corr = (G.ord.kclose > 0.f);
+    const bool defer = (fastv && use_corr) || ((nsplit > 32) && (n_iblocks * 8 <= slots) && (vi.ib > 4) && !herm);
     a.defer_reduce = defer ? 1 : 0;
     a.eps2 = eps2;
-    if (nsplit > 1) ensure_partials((size_t)nsplit * ni);
+    if (nsplit > 1 || (fastv && use_corr)) ensure_partials((size_t)nsplit * ni);
+    if (use_corr) {
+        ensure_close_buffers(ni, fastv);
+        a.corr = G.d_corr;
+        if (fastv) {
+            a.wl = G.d_wl;
+            a.wl_count = G.d_wl_count;
+            a.wl_cap = (unsigned int)G.wl_cap;
+        }
+    }
     a.part_sum = G.part_sum; a.part_key = G.part_key;
     a.tickets = G.tickets;
     a.out_sum = out_sum; a.out_key = out_key; a.out_nnid = out_nnid;
@@ -881,6 +944,11 @@ void launch_force(int nj, int ni, const IBlock &ib, float eps2, bool nn, bool li
             exit(-1);
     }
     G.launches++;
+    if (fastv && use_corr) {
+        close_pairs_kernel<<<G.sm_count * 4, 256, 0, G.stream>>>(a);
+        CK(cudaGetLastError());
+        G.launches++;
+    }
     if (defer) {
         reduce_partials_kernel<<<reduce_ctas, 256, 0, G.stream>>>(a, nn ? 1 : 0);
         CK(cudaGetLastError());
@@ -905,7 +973,9 @@ void free_all()
     G.order_valid = false; G.order_nj = -1; G.ids_dirty = false;
     G.updates_since_order = G.updates_since_force = 0;
     G.h_slot_of.clear(); G.h_id.clear(); G.h_perm.clear();
-    dev_free(G.d_conf); dev_free(G.d_conf2);
+    dev_free(G.d_conf); dev_free(G.d_conf2); dev_free(G.d_stats);
+    dev_free(G.d_wl); dev_free(G.d_wl_count); dev_free(G.d_corr);
+    G.wl_cap = G.corr_cap = 0;
     dev_free(G.d_ikey); dev_free(G.d_ikey_tmp); dev_free(G.d_iperm); dev_free(G.d_iperm_tmp);
     G.isort_cap = 0;
     dev_free(G.d_up);
@@ -1077,6 +1147,7 @@ static void open_context(int dev)   // g_cur selected by the caller
         e = getenv("G6_B200_FARC");
         G.farc = (e && *e) ? (float)atof(e) : 0.125f;
         G.near_w = std::max(1, env_int("G6_B200_NEAR_WINDOW", 32));
+        G.wl_per_i = std::max(1, env_int("G6_B200_WL_PER_I", 512));
     }
     host_alloc(G.h_i, (size_t)4 * G.npipes);
     dev_alloc(G.d_i, (size_t)4 * G.npipes);
@@ -1655,13 +1726,35 @@ int g6x_set_close_factor(double k_close, double far_factor)
         Context &c = g_ctx[k];
         if (k_close >= 0.0) c.kclose = (float)k_close;
         if (far_factor >= 0.0) c.farc = (float)far_factor;
-        c.ord.kclose = c.kclose;
+        c.ord.kclose = (c.order_tiny && c.kclose > 0.f) ? 1.0e30f : c.kclose;
         c.ord.farc2 = c.farc * c.farc;
     }
     return 0;
 }
 
 long long g6x_order_rebuilds(void) { return g_ctx[0].order_rebuilds; }
+
+// (warp x group) blocks the speculative kernel took FAR / NEAR / CLOSE and NEAR blocks it redid, since the last
+// call (device 0).  Counted only by builds with -DG6_STATS (returns 0 there, -1 otherwise).
+int g6x_block_stats(unsigned long long out[4])
+{
+    require_open("g6x_block_stats");
+    for (int m = 0; m < 4; m++) out[m] = 0;
+#ifdef G6_STATS
+    use(0);
+    CK(cudaStreamSynchronize(G.stream));
+    if (!G.d_stats) {
+        dev_alloc(G.d_stats, 4);
+        CK(cudaMemset(G.d_stats, 0, 4 * sizeof(unsigned long long)));
+        return 0;
+    }
+    CK(cudaMemcpy(out, G.d_stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    CK(cudaMemset(G.d_stats, 0, 4 * sizeof(unsigned long long)));
+    return 0;
+#else
+    return -1;
+#endif
+}
 int g6x_device_count_open(void) { return M.n; }
 
 int g6x_set_j_offset(int offset)
@@ -2287,6 +2380,11 @@ long long g6x_hermite_evolve(int nj, double t_end, double eta, double eps2, long
         g6x_hermite_step(nj, ni, ilist.data(), tnext, eta, eps2, olddt.data(), newdt.data(), nullptr, nullptr);
         for (int k = 0; k < ni; k++) {
             const int j = ilist[k];
+            if (!(newdt[k] > 0.0) || !std::isfinite(newdt[k])) {
+                fprintf(stderr, "g6_b200: FATAL g6x_hermite_evolve: particle %d got time step %g at t = %.17g\n", j,
+                        newdt[k], tnext);
+                exit(-1);
+            }
             H.time[j] = tnext;
             H.dt[j] = newdt[k];
             heap.push_back(Ev(tnext + newdt[k], j));

@@ -37,6 +37,7 @@ constexpr int TILE = 256;      // j-particles per shared-memory stage
 constexpr int STAGES = 3;      // TMA bulk-copy pipeline depth
 constexpr int GROUPS_PER_TILE = TILE / 32;
 constexpr int TBOX = 2 * GROUPS_PER_TILE + 2;   // float4 per tile in gbb: 8 group boxes + the tile's own box
+constexpr int CTA_WL = 768;    // FP64 pairs a CTA of a masked kernel can queue (more are evaluated in place)
 #ifndef G6_FLUSH
 #define G6_FLUSH 16
 #endif
@@ -473,6 +474,17 @@ struct ForceArgs {
     int *conf;                    // [ni] slot of the j-particle with particle i's id (-1 none, -2 several): read by the
                                   // speculative kernel (near_kernel wrote it), written by the masked kernels
     const int *iperm;             // outputs of packed particle i go to index iperm[i] (NULL: i)
+    unsigned long long *stats;    // -DG6_STATS builds: (warp x group) blocks taken FAR / NEAR / CLOSE, NEAR redone
+    // FP64 pairs are not evaluated where they are found (one lane of a warp would hold up the other 31 for a
+    // thousand cycles: FP64 issues at 1/64 of the FP32 rate on this chip) but collected and evaluated densely,
+    // one pair per thread: the speculative kernel appends (packed i, slot) to a global list that
+    // close_pairs_kernel works off, the masked kernels keep a list per CTA in shared memory.  Either way the
+    // results are added into corr[] with FP64 atomics, and whoever writes particle i's outputs adds corr[i]
+    // (and clears it for the next launch).
+    int2 *wl;                     // global list (speculative kernel)
+    unsigned int *wl_count;       // entries appended (zero between launches)
+    unsigned int wl_cap;
+    double *corr;                 // [ni][7], zero between launches (NULL: FP64 pairs are evaluated in place)
     double *part_sum;             // [nsplit][ni_pad][7]
     u64 *part_key;                // [nsplit][ni_pad]   (min r2 bits << 32 | slot)
     unsigned int *tickets;        // [gridDim.y], zero between launches
@@ -512,8 +524,18 @@ __device__ __forceinline__ void hermite_correct_one(const HermiteArgs &h, const 
 // Final outputs of particle i (local arrays + the peers' exchange slots).  kk carries a slot of this
 // launch's j-window; what leaves the kernel carries the address the caller gave that particle.
 template <bool NN, bool HERM = false>
-__device__ __forceinline__ void store_outputs(const ForceArgs &p, const int i, const double *tot, const u64 kk)
+__device__ __forceinline__ void store_outputs(const ForceArgs &p, const int i, const double *tot_in, const u64 kk)
 {
+    double tot[7];
+#pragma unroll
+    for (int q = 0; q < 7; q++) tot[q] = tot_in[q];
+    if (p.corr) {   // the FP64 pairs of this particle (all of them: their atomics precede this point, see ForceArgs)
+#pragma unroll
+        for (int q = 0; q < 7; q++) {
+            tot[q] += __ldcg(p.corr + (size_t)i * 7 + q);
+            p.corr[(size_t)i * 7 + q] = 0.0;
+        }
+    }
     int id = -1;
     u64 ko = KEY_NONE;
     if (NN && kk != KEY_NONE) {
@@ -596,6 +618,23 @@ __device__ __noinline__ void fp64_pair(F64Out *o, const float4 a, const float4 b
     fp64_accumulate(o->v, ((double)a.x + (double)b.x) - xi, ((double)a.y + (double)b.y) - yi,
                     ((double)a.z + (double)b.z) - zi, ((double)c.x + (double)l.x) - vxi, ((double)c.y + (double)l.y) - vyi,
                     ((double)c.z + (double)l.z) - vzi, (double)a.w + (double)l.w, eps2t);
+}
+
+// FP64 pair (packed particle i, slot j of the launch's window) added into corr[i] with atomics.
+__device__ __forceinline__ void close_pair_to_corr(const ForceArgs &p, const float4 ia, const float4 ib, const float4 ic,
+                                                   const float4 id, const int i, const int j)
+{
+    const float4 a = p.jA[j], b = p.jB[j], c = p.jC[j], l = p.jL[j];
+    double v[7] = {0, 0, 0, 0, 0, 0, 0};
+    fp64_accumulate(v, ((double)a.x + (double)b.x) - ((double)ia.x + (double)ib.x),
+                    ((double)a.y + (double)b.y) - ((double)ia.y + (double)ib.y),
+                    ((double)a.z + (double)b.z) - ((double)ia.z + (double)ib.z),
+                    ((double)c.x + (double)l.x) - ((double)ic.x + (double)id.x),
+                    ((double)c.y + (double)l.y) - ((double)ic.y + (double)id.y),
+                    ((double)c.z + (double)l.z) - ((double)ic.z + (double)id.z), (double)a.w + (double)l.w,
+                    (double)p.eps2 + (double)TINYF);
+#pragma unroll
+    for (int q = 0; q < 7; q++) atomicAdd(p.corr + (size_t)i * 7 + q, v[q]);
 }
 
 struct Acc7 {
@@ -871,6 +910,8 @@ struct __align__(16) ForceSmem {
     float4 G[STAGES][TBOX];   // group boxes + tile box (speculative kernel only)
     uint64_t full[STAGES];
     unsigned int is_last;
+    unsigned int wl_n;        // masked kernels: FP64 pairs found by this CTA
+    int2 wl[CTA_WL];          // (packed i, slot)
 };
 
 __device__ __forceinline__ u64 make_key(float r2min, int jmin)
@@ -916,6 +957,7 @@ __global__ void __launch_bounds__(THREADS, MINB) force_kernel(const __grid_const
     if (tid == 0) {
         for (int s = 0; s < STAGES; s++) mbar_init(&sm.full[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        sm.wl_n = 0u;
     }
     __syncthreads();
     constexpr uint32_t STAGE_BYTES = 3u * TILE * sizeof(float4);
@@ -962,9 +1004,17 @@ __global__ void __launch_bounds__(THREADS, MINB) force_kernel(const __grid_const
         }
     }
     const double eps2t = (double)p.eps2 + (double)TINYF;
-    // pair (k, slot j of this launch's window) in FP64, added to D[k] (rare: a handful of pairs per particle)
+    // pair (k, slot j of this launch's window) to be evaluated in FP64: queued for the dense pass after the tile
+    // loop; without a corr buffer (or with the queue full) evaluated here and added to D[k]
     auto close_pair = [&](const int k, const float4 a, const float4 b, const float4 c, const int jlocal, double *Dk) {
         const int i = i_of(k);
+        if (p.corr) {
+            const unsigned int e = atomicAdd(&sm.wl_n, 1u);
+            if (e < (unsigned)CTA_WL) {
+                sm.wl[e] = make_int2(i, jlocal);
+                return;
+            }
+        }
         const float4 d = (INL > 0) ? ii.d[3 * INL + i] : p.iD[i];
         F64Out o;
         fp64_pair(&o, a, b, c, p.jL[jlocal], (double)xh[k] + (double)xl[k], (double)yh[k] + (double)yl[k],
@@ -1104,6 +1154,19 @@ __global__ void __launch_bounds__(THREADS, MINB) force_kernel(const __grid_const
         }
     }
 
+    // ---- dense pass over the FP64 pairs this CTA queued: one pair per thread ----------------------
+    if (p.corr) {
+        __syncthreads();
+        const unsigned int nwl = sm.wl_n < (unsigned)CTA_WL ? sm.wl_n : (unsigned)CTA_WL;
+        for (unsigned int e = tid; e < nwl; e += THREADS) {
+            const int2 w = sm.wl[e];
+            const float4 ia = (INL > 0) ? ii.d[w.x] : p.iA[w.x], ib = (INL > 0) ? ii.d[INL + w.x] : p.iB[w.x],
+                         ic = (INL > 0) ? ii.d[2 * INL + w.x] : p.iC[w.x], id = (INL > 0) ? ii.d[3 * INL + w.x] : p.iD[w.x];
+            close_pair_to_corr(p, ia, ib, ic, id, w.x, w.y);
+        }
+        __threadfence();   // the atomics precede this CTA's ticket / final stores
+    }
+
     // ---- keys (slot of this launch's j-window) --------------------------------
     u64 key[IPT];
 #pragma unroll
@@ -1193,9 +1256,10 @@ __global__ void __launch_bounds__(THREADS, MINB) force_kernel(const __grid_const
 //          neighbour search; a group whose minimum is not above R2_EXACT is redone exactly;
 //   CLOSE  some particle of the warp has the group's box inside its FP64 radius, or the j-particle that
 //          carries the id of one of the warp's particles sits in the group (conf[], from the id table), or
-//          the group is the ragged tail: the whole block is evaluated in FP64 exactly as the reference does
-//          (idata.cc:206-233: equal ids skipped, pot and neighbour search only for r2 > 2^-52), each lane
-//          predicting one j from the FP64 state and broadcasting it by shuffles.
+//          the group is the ragged tail: the block is evaluated pair by pair with the reference's rule
+//          (idata.cc:206-233: equal ids skipped, pot and neighbour search only for r2 > 2^-52), and every pair
+//          closer than its i-particle's FP64 radius is left out of the FP32 sums and queued for
+//          close_pairs_kernel, which evaluates the queue densely in FP64 (one pair per thread).
 // Results are therefore those of the masked rule for every input, and the pairs that dominate a
 // particle's acc and jerk never see FP32 rounding.  The nearest neighbour is kept as (min r2, first group
 // that lowered it); the exact j is found at the end by re-scanning that one group with the same r2
@@ -1283,66 +1347,52 @@ __device__ __forceinline__ u64 interact2_fast(const float4 a, const float4 b, co
     return r2;
 }
 
-// FP64 evaluation of one group of up to 32 j against one packed i-pair (CLOSE blocks).  Lane l converts
-// j = first + l of the tile to doubles and the warp walks the group by shuffles.
-// Not inlined: its registers must not weigh on the FP32 loop.
-struct F64Group {
-    double v[2][7];
-    float rmin[2];
-};
-__device__ __noinline__ void fp64_group(F64Group *o, const ForceArgs *p, const int jfirst, const int count,
-                                        const float4 *tA, const float4 *tB, const float4 *tC, const IPair ip,
-                                        const int i0)
+// FP64 pairs the speculative kernel queued, one per thread (grid-stride over the list).  A lane queued all pairs
+// of one particle back to back, so a warp mostly holds runs of equal i: each run is summed with shuffles and
+// its head lane issues the seven atomics.
+__global__ void __launch_bounds__(256) close_pairs_kernel(const ForceArgs p)
 {
+    const unsigned int n = min(*p.wl_count, p.wl_cap);
+    const unsigned int nround = (n + 31u) & ~31u;   // whole warps stay in the loop
     const int lane = threadIdx.x & 31;
-    const float4 ja = tA[lane], jb = tB[lane], jc = tC[lane];
-    const float4 jl = p->jL[jfirst + lane];   // inside the padded arrays even when lane >= count
-    const int myid = __float_as_int(jb.w);
-    const double mym = (lane < count && ja.w > 0.f) ? (double)ja.w + (double)jl.w : 0.0;   // massless j: skipped (idata.cc:208)
-    const double mx = (double)ja.x + (double)jb.x, my = (double)ja.y + (double)jb.y, mz = (double)ja.z + (double)jb.z;
-    const double mvx = (double)jc.x + (double)jl.x, mvy = (double)jc.y + (double)jl.y, mvz = (double)jc.z + (double)jl.z;
-    float h0, h1, l0, l1;
-    double xi[2], yi[2], zi[2], vxi[2], vyi[2], vzi[2];
-    upk(ip.nxh, h0, h1); upk(ip.nxl, l0, l1); xi[0] = -((double)h0 + (double)l0); xi[1] = -((double)h1 + (double)l1);
-    upk(ip.nyh, h0, h1); upk(ip.nyl, l0, l1); yi[0] = -((double)h0 + (double)l0); yi[1] = -((double)h1 + (double)l1);
-    upk(ip.nzh, h0, h1); upk(ip.nzl, l0, l1); zi[0] = -((double)h0 + (double)l0); zi[1] = -((double)h1 + (double)l1);
-    const float4 d0 = (i0 < p->ni) ? p->iD[i0] : make_float4(0.f, 0.f, 0.f, 0.f);
-    const float4 d1 = (i0 + 1 < p->ni) ? p->iD[i0 + 1] : make_float4(0.f, 0.f, 0.f, 0.f);
-    upk(ip.nvx, h0, h1); vxi[0] = (double)d0.x - (double)h0; vxi[1] = (double)d1.x - (double)h1;
-    upk(ip.nvy, h0, h1); vyi[0] = (double)d0.y - (double)h0; vyi[1] = (double)d1.y - (double)h1;
-    upk(ip.nvz, h0, h1); vzi[0] = (double)d0.z - (double)h0; vzi[1] = (double)d1.z - (double)h1;
-    const double eps2t = (double)p->eps2 + (double)TINYF;
-    double v0[7] = {0, 0, 0, 0, 0, 0, 0}, v1[7] = {0, 0, 0, 0, 0, 0, 0};
-    float rm0 = __int_as_float(0x7f800000), rm1 = rm0;
-    for (int u = 0; u < count; u++) {
-        const double m = __shfl_sync(0xffffffffu, mym, u);
-        if (m == 0.0) continue;   // warp-uniform
-        const double xj = __shfl_sync(0xffffffffu, mx, u), yj = __shfl_sync(0xffffffffu, my, u),
-                     zj = __shfl_sync(0xffffffffu, mz, u);
-        const double vxj = __shfl_sync(0xffffffffu, mvx, u), vyj = __shfl_sync(0xffffffffu, mvy, u),
-                     vzj = __shfl_sync(0xffffffffu, mvz, u);
-        const int jid = __shfl_sync(0xffffffffu, myid, u);
-        // neighbour search on the FP32 r2 every other path uses
-        u64 dx, dy, dz, r2;
-        pair_geometry(tA[u], tB[u], ip, dx, dy, dz, r2);
-        float r20, r21;
-        upk(r2, r20, r21);
-        if (jid != ip.id0) {
-            if (r20 > TINYF) rm0 = fminf(rm0, r20);
-            fp64_accumulate(v0, xj - xi[0], yj - yi[0], zj - zi[0], vxj - vxi[0], vyj - vyi[0], vzj - vzi[0], m, eps2t);
+    for (unsigned int e = blockIdx.x * blockDim.x + threadIdx.x; e < nround; e += gridDim.x * blockDim.x) {
+        int i = -1 - lane;   // lanes past the end: distinct negative ids, no contribution
+        double v[7] = {0, 0, 0, 0, 0, 0, 0};
+        if (e < n) {
+            const int2 w = p.wl[e];
+            i = w.x;
+            const float4 ia = p.iA[i], ib = p.iB[i], ic = p.iC[i], id = p.iD[i];
+            const float4 a = p.jA[w.y], b = p.jB[w.y], c = p.jC[w.y], l = p.jL[w.y];
+            fp64_accumulate(v, ((double)a.x + (double)b.x) - ((double)ia.x + (double)ib.x),
+                            ((double)a.y + (double)b.y) - ((double)ia.y + (double)ib.y),
+                            ((double)a.z + (double)b.z) - ((double)ia.z + (double)ib.z),
+                            ((double)c.x + (double)l.x) - ((double)ic.x + (double)id.x),
+                            ((double)c.y + (double)l.y) - ((double)ic.y + (double)id.y),
+                            ((double)c.z + (double)l.z) - ((double)ic.z + (double)id.z), (double)a.w + (double)l.w,
+                            (double)p.eps2 + (double)TINYF);
         }
-        if (jid != ip.id1) {
-            if (r21 > TINYF) rm1 = fminf(rm1, r21);
-            fp64_accumulate(v1, xj - xi[1], yj - yi[1], zj - zi[1], vxj - vxi[1], vyj - vyi[1], vzj - vzi[1], m, eps2t);
-        }
-    }
+        // segmented sum over the runs of equal i (a run = consecutive lanes; the same i may come back in a later
+        // run, so lanes are matched by run number, not by i): after the last step the first lane of a run holds
+        // its sum
+        const int iprev = __shfl_up_sync(0xffffffffu, i, 1);
+        const bool head = (lane == 0) || (iprev != i);
+        const unsigned int heads = __ballot_sync(0xffffffffu, head);
+        const int run = __popc(heads & (0xffffffffu >> (31 - lane)));
 #pragma unroll
-    for (int q = 0; q < 7; q++) {
-        o->v[0][q] = v0[q];
-        o->v[1][q] = v1[q];
+        for (int off = 1; off < 32; off <<= 1) {
+            const int ro = __shfl_down_sync(0xffffffffu, run, off);
+            const bool take = (lane + off < 32) && (ro == run);
+#pragma unroll
+            for (int q = 0; q < 7; q++) {
+                const double o = __shfl_down_sync(0xffffffffu, v[q], off);
+                if (take) v[q] += o;
+            }
+        }
+        if (i >= 0 && head) {
+#pragma unroll
+            for (int q = 0; q < 7; q++) atomicAdd(p.corr + (size_t)i * 7 + q, v[q]);
+        }
     }
-    o->rmin[0] = rm0;
-    o->rmin[1] = rm1;
 }
 
 // Pre-pass of the speculative kernel, one thread per packed i-particle: the slot of the j-particle that
@@ -1489,6 +1539,9 @@ __global__ void __launch_bounds__(THREADS, MINB) force_fast_kernel(const __grid_
     }
     const float eps2 = p.eps2 + TINYF;   // the reference softens by eps2 + 2^-52 (idata.cc:216)
     const u64 eps2p = pk(eps2, eps2);
+#ifdef G6_STATS
+    unsigned int nmode[4] = {0u, 0u, 0u, 0u};
+#endif
 
     for (int t = 0; t < ntiles; t++) {
         const int s = t % STAGES;
@@ -1579,33 +1632,84 @@ __global__ void __launch_bounds__(THREADS, MINB) force_fast_kernel(const __grid_
                 bool bad = false;
 #pragma unroll
                 for (int k = 0; k < IPT; k++) bad |= !(rmin[k] > R2_EXACT);
-                if (__any_sync(0xffffffffu, bad)) mode = 2;   // a pair too close for the mask-free path
-            }
-            if (mode == 2) {
-                const int n = (cnt - jj0 < GRP) ? cnt - jj0 : GRP;
-#pragma unroll
-                for (int q = 0; q < NP; q++) {
-                    F64Group o;
-                    fp64_group(&o, &p, jtile + jj0, n, tA + jj0, tB + jj0, tC + jj0, IP[q], i_of(2 * q));
-#pragma unroll
-                    for (int c = 0; c < 7; c++) {
-                        D[2 * q][c] += o.v[0][c];
-                        D[2 * q + 1][c] += o.v[1][c];
-                    }
-                    rmin[2 * q] = o.rmin[0];
-                    rmin[2 * q + 1] = o.rmin[1];
+                if (__any_sync(0xffffffffu, bad)) {   // a pair too close for the mask-free path
+                    mode = 2;
+#ifdef G6_STATS
+                    nmode[3]++;
+#endif
                 }
-            } else {
-                // the mask-free pair function accumulates -acc, -jerk
+            }
+#ifdef G6_STATS
+            nmode[mode]++;
+#endif
+            if (mode == 2) {
+                // the reference's rule pair by pair (equal ids skipped, pot and neighbour search only for
+                // r2 > 2^-52) in FP32; pairs inside a particle's FP64 radius are left out of the sums and queued
+#pragma unroll
+                for (int q = 0; q < NP; q++) S[q] = Acc7P{0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull};
+#pragma unroll
+                for (int k = 0; k < IPT; k++) rmin[k] = INF;
+                const int jend = (jj0 + GRP < cnt) ? jj0 + GRP : cnt;
+                unsigned int hpm[IPT];   // bit u: pair (particle k, j = jj0 + u) is inside k's FP64 radius
+#pragma unroll
+                for (int k = 0; k < IPT; k++) hpm[k] = 0u;
+                for (int jj = jj0; jj < jend; jj++) {
+                    const float4 a = tA[jj], b = tB[jj], c = tC[jj];
+                    int unused0 = 0, unused1 = 0;
+#pragma unroll
+                    for (int q = 0; q < NP; q++) {
+                        const int hp = interact2<true, false, NR, false>(a, b, c, 0, IP[q], eps2p, closek[2 * q],
+                                                                         closek[2 * q + 1], S[q], rmin[2 * q], unused0,
+                                                                         rmin[2 * q + 1], unused1, 0, p);
+                        hpm[2 * q] |= (unsigned)(hp & 1) << (jj - jj0);
+                        hpm[2 * q + 1] |= (unsigned)((hp >> 1) & 1) << (jj - jj0);
+                    }
+                }
+                // queue the block's FP64 pairs with ONE atomic: warp prefix sum of the lanes' counts
+                int mine = 0;
+#pragma unroll
+                for (int k = 0; k < IPT; k++) mine += __popc(hpm[k]);
+                if (__any_sync(0xffffffffu, mine != 0)) {
+                    const int lane = tid & 31;
+                    int incl = mine;
+#pragma unroll
+                    for (int off = 1; off < 32; off <<= 1) {
+                        const int o = __shfl_up_sync(0xffffffffu, incl, off);
+                        if (lane >= off) incl += o;
+                    }
+                    const int total = __shfl_sync(0xffffffffu, incl, 31);
+                    unsigned int base = 0u;
+                    if (lane == 0) base = atomicAdd(p.wl_count, (unsigned)total);
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    unsigned int pos = base + (unsigned)(incl - mine);
+#pragma unroll
+                    for (int k = 0; k < IPT; k++) {
+                        const int i = i_of(k);
+                        unsigned int m = hpm[k];
+                        while (m) {
+                            const int u = __ffs(m) - 1;
+                            m &= m - 1u;
+                            if (pos < p.wl_cap) {
+                                p.wl[pos] = make_int2(i, jtile + jj0 + u);
+                            } else {   // list full: evaluate here
+                                close_pair_to_corr(p, p.iA[i], p.iB[i], p.iC[i], p.iD[i], i, jtile + jj0 + u);
+                            }
+                            pos++;
+                        }
+                    }
+                }
+            }
+            {
+                const double sg = (mode == 2) ? 1.0 : -1.0;   // the mask-free pair function accumulates -acc, -jerk
 #pragma unroll
                 for (int q = 0; q < NP; q++) {
                     float lo, hi;
-                    upk(S[q].ax, lo, hi); D[2 * q][0] -= (double)lo; D[2 * q + 1][0] -= (double)hi;
-                    upk(S[q].ay, lo, hi); D[2 * q][1] -= (double)lo; D[2 * q + 1][1] -= (double)hi;
-                    upk(S[q].az, lo, hi); D[2 * q][2] -= (double)lo; D[2 * q + 1][2] -= (double)hi;
-                    upk(S[q].jx, lo, hi); D[2 * q][3] -= (double)lo; D[2 * q + 1][3] -= (double)hi;
-                    upk(S[q].jy, lo, hi); D[2 * q][4] -= (double)lo; D[2 * q + 1][4] -= (double)hi;
-                    upk(S[q].jz, lo, hi); D[2 * q][5] -= (double)lo; D[2 * q + 1][5] -= (double)hi;
+                    upk(S[q].ax, lo, hi); D[2 * q][0] += sg * (double)lo; D[2 * q + 1][0] += sg * (double)hi;
+                    upk(S[q].ay, lo, hi); D[2 * q][1] += sg * (double)lo; D[2 * q + 1][1] += sg * (double)hi;
+                    upk(S[q].az, lo, hi); D[2 * q][2] += sg * (double)lo; D[2 * q + 1][2] += sg * (double)hi;
+                    upk(S[q].jx, lo, hi); D[2 * q][3] += sg * (double)lo; D[2 * q + 1][3] += sg * (double)hi;
+                    upk(S[q].jy, lo, hi); D[2 * q][4] += sg * (double)lo; D[2 * q + 1][4] += sg * (double)hi;
+                    upk(S[q].jz, lo, hi); D[2 * q][5] += sg * (double)lo; D[2 * q + 1][5] += sg * (double)hi;
                     upk(S[q].pot, lo, hi); D[2 * q][6] += (double)lo; D[2 * q + 1][6] += (double)hi;
                 }
             }
@@ -1624,6 +1728,10 @@ __global__ void __launch_bounds__(THREADS, MINB) force_fast_kernel(const __grid_
         if (tid == 0 && t + STAGES < ntiles) issue_stage(s, tile0 + t + STAGES);
     }
 
+#ifdef G6_STATS
+    if (p.stats && (tid & 31) == 0)
+        for (int m = 0; m < 4; m++) atomicAdd(&p.stats[m], (unsigned long long)nmode[m]);
+#endif
     // ---- nearest neighbour: re-scan the one group that holds the minimum ---------------------
     u64 key[IPT];
 #pragma unroll
@@ -1648,7 +1756,9 @@ __global__ void __launch_bounds__(THREADS, MINB) force_fast_kernel(const __grid_
     }
 
     // ---- totals -> global (final or per-split partial) -----------------------------------
-    const bool single = (p.nsplit == 1);
+    // (with the FP64 pair list in use the launch always ends at the partials: close_pairs_kernel and
+    // reduce_partials_kernel follow)
+    const bool single = (p.nsplit == 1) && !p.corr;
 #pragma unroll
     for (int k = 0; k < IPT; k++) {
         const int i = i_of(k);
@@ -1673,6 +1783,7 @@ __global__ void __launch_bounds__(THREADS, MINB) force_fast_kernel(const __grid_
 // and a fixed butterfly of shuffles combines them (deterministic).
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const ForceArgs p, const int want_nn)
 {
+    if (p.wl_count && blockIdx.x == 0 && threadIdx.x == 0) *p.wl_count = 0u;   // close_pairs_kernel is done with it
     const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (i < p.ni) {
@@ -1739,18 +1850,21 @@ __global__ void resolve_nn_kernel(int ni, const u64 *__restrict__ key, int rank,
 // ---------------------------------------------------------------------------
 // j-memory order (host: rebuild_order): bounding box, Morton keys, permutation, id table, neighbour bounds.
 // ---------------------------------------------------------------------------
-// box[0..2] = min, box[3..5] = max of the positions of the massive particles with address < nj (ordered ints)
+// box[0..2] = min, box[3..5] = max of the positions of the massive particles with address < nj (ordered ints);
+// cen[0..2] = sum of their positions, cen[3] = their number (the origin is their mean: the lo parts of the
+// double-single coordinates are smallest where the particles are)
 __global__ void __launch_bounds__(256) order_box_kernel(const int n, const int nj, const JState s, const int *addr_of,
-                                                        int *box)
+                                                        int *box, double *cen)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const bool use = (j < n) && (addr_of[j] < nj) && (s.q[6][j].y > (double)TINYF);
-    float x = 0.f, y = 0.f, z = 0.f;
+    double xd = 0.0, yd = 0.0, zd = 0.0, cnt = use ? 1.0 : 0.0;
     if (use) {
-        x = (float)s.q[0][j].x;
-        y = (float)s.q[0][j].y;
-        z = (float)s.q[1][j].x;
+        xd = s.q[0][j].x;
+        yd = s.q[0][j].y;
+        zd = s.q[1][j].x;
     }
+    const float x = (float)xd, y = (float)yd, z = (float)zd;
     const int big = 0x7f7fffff, small = f2ord(-3.0e38f);
     int v[6] = {use ? f2ord(x) : big, use ? f2ord(y) : big, use ? f2ord(z) : big,
                 use ? f2ord(x) : small, use ? f2ord(y) : small, use ? f2ord(z) : small};
@@ -1759,12 +1873,23 @@ __global__ void __launch_bounds__(256) order_box_kernel(const int n, const int n
         v[d] = __reduce_min_sync(0xffffffffu, v[d]);
         v[3 + d] = __reduce_max_sync(0xffffffffu, v[3 + d]);
     }
-    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        xd += __shfl_xor_sync(0xffffffffu, xd, off);
+        yd += __shfl_xor_sync(0xffffffffu, yd, off);
+        zd += __shfl_xor_sync(0xffffffffu, zd, off);
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+    }
+    if ((threadIdx.x & 31) == 0 && cnt > 0.0) {
 #pragma unroll
         for (int d = 0; d < 3; d++) {
             atomicMin(&box[d], v[d]);
             atomicMax(&box[3 + d], v[3 + d]);
         }
+        atomicAdd(&cen[0], xd);
+        atomicAdd(&cen[1], yd);
+        atomicAdd(&cen[2], zd);
+        atomicAdd(&cen[3], cnt);
     }
 }
 // sort keys: Morton key of the position (relative to x0) for massive particles of the prefix [0, nj);
@@ -1787,14 +1912,15 @@ __global__ void __launch_bounds__(256) order_key_kernel(const int n, const int n
     key[j] = k;
     val[j] = j;
 }
-// new slot j takes what old slot perm[j] held
-__global__ void __launch_bounds__(256) order_permute_kernel(const int n, const int *__restrict__ perm, const JState from,
-                                                            const int *__restrict__ addr_from, JState to, int *addr_to,
-                                                            int *slot_of)
+// new slot j < n takes what old slot perm[j] held; slots [n, ncap) are copied as they are (the two sets of
+// arrays swap roles afterwards, so every slot of the capacity must arrive in the target set)
+__global__ void __launch_bounds__(256) order_permute_kernel(const int n, const int ncap, const int *__restrict__ perm,
+                                                            const JState from, const int *__restrict__ addr_from,
+                                                            JState to, int *addr_to, int *slot_of)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
-    const int o = perm[j];
+    if (j >= ncap) return;
+    const int o = j < n ? perm[j] : j;
 #pragma unroll
     for (int k = 0; k < 7; k++) to.q[k][j] = from.q[k][o];
     to.ia[j] = from.ia[o];
@@ -1894,7 +2020,10 @@ __device__ __forceinline__ void hermite_correct_one(const HermiteArgs &h, const 
         int exponent;
         const double olddt = h.olddt_d[i];
         double oldstep2 = olddt / (2 * frexp(olddt, &exponent));
-        while (fmod(h.tnext, oldstep2) != 0) oldstep2 /= 2;
+        // (bounded: a step that is not a positive power of two -- a caller error or a NaN force -- must not
+        // hang the device; the host sees the NaN step and stops)
+        for (int it = 0; it < 1200 && fmod(h.tnext, oldstep2) != 0; it++) oldstep2 /= 2;
+        if (!(olddt > 0.0) || !(oldstep2 > 0.0)) oldstep2 = __longlong_as_double(0x7ff8000000000000ll);
         if (newstep < oldstep2) {
             newstep = oldstep2 / 2;
         } else {
@@ -1913,8 +2042,8 @@ __device__ __forceinline__ void hermite_correct_one(const HermiteArgs &h, const 
         if (first != first) first = fac * h.eta;
         int exponent;
         first /= 2 * frexp(first, &exponent);
-        while (fmod(h.tnext, first) != 0) first /= 2;
-        while (first > limit) first /= 2;
+        for (int it = 0; it < 1200 && fmod(h.tnext, first) != 0; it++) first /= 2;
+        for (int it = 0; it < 1200 && first > limit; it++) first /= 2;
         newstep = first;
     }
     s.q[0][a] = make_double2(pos[0], pos[1]);

@@ -154,6 +154,10 @@ int g6x_set_refine(int on);
 int g6x_set_close_factor(double k_close, double far_factor);
 /* How often the j-memory has been re-ordered (Morton sort + id table) since g6_open_. */
 long long g6x_order_rebuilds(void);
+/* Diagnostics of the pair classification: (warp of i) x (group of j) blocks taken FAR / NEAR / CLOSE and NEAR
+ * blocks redone exactly, since the previous call.  Only builds with -DG6_STATS count (returns 0; the first
+ * call arms the counters); the production build returns -1. */
+int g6x_block_stats(unsigned long long out[4]);
 /* Devices g6_open_ opened (G6_B200_DEVICES; 0 when closed). */
 int g6x_device_count_open(void);
 /* This process owns j-addresses whose GLOBAL address is local + offset (used

@@ -7,6 +7,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 GOLDEN = os.path.join(ROOT, "tests", "golden")
+# a kernel that never raises its completion flag must end the test run, not hang it (the library itself
+# waits without limit unless told otherwise)
+os.environ.setdefault("G6_B200_WAIT_SECONDS", "120")
 
 
 def pytest_configure(config):

@@ -34,7 +34,7 @@ def check_forces(got, ref, tol=TOL, what=""):
     ep = rel_err(got["pot"], ref["pot"])
     assert ea.max() <= tol, "%s acc rel err %.3e" % (what, ea.max())
     assert ep.max() <= tol, "%s pot rel err %.3e" % (what, ep.max())
-    assert ej.max() <= TOL_JERK_MAX, "%s jerk rel err max %.3e" % (what, ej.max())
+    assert ej.max() <= min(tol, TOL_JERK_MAX) if tol < TOL else ej.max() <= max(tol, TOL_JERK_MAX), "%s jerk rel err max %.3e" % (what, ej.max())
     if "sjerk" in ref:
         sc = np.linalg.norm(got["jerk"] - ref["jerk"], axis=1) / ref["sjerk"]
         assert sc.max() <= TOL_JERK_SCALED, "%s jerk err / sum|terms| %.3e" % (what, sc.max())

@@ -185,7 +185,10 @@ def test_speculative_kernel_equals_masked_kernel(g6, variant):
             # mask or a lost group would show as an O(1) difference
             assert rel_vec_err(out["acc"], masked["acc"]).max() < 1e-6
             assert rel_err(out["pot"], masked["pot"]).max() < 1e-6
-            assert np.array_equal(out_nonn["acc"], out["acc"]) and np.array_equal(out_nonn["pot"], out["pot"])
+            # lasthalf without the neighbour output: the same launch (the pairs evaluated in FP64 are added with
+            # atomics, so two runs agree to FP64 rounding of a sum, not bit for bit)
+            assert rel_vec_err(out_nonn["acc"], out["acc"]).max() < 1e-12
+            assert rel_err(out_nonn["pot"], out["pot"]).max() < 1e-12
 
 
 def test_j_update_visible_and_last_write_wins(g6):
@@ -399,7 +402,16 @@ def test_close_open_cycle(g6):
         _fresh(g6, ids, m, x, v)
         out = g6.calc(ids[:32], x[:32], v[:32], 1e-4)
         check_forces(out, ref, what="reopen")
-    assert g6.L.g6_open_(C.byref(C.c_int(4096))) == -1      # no such device (sapporo.cpp:31-34)
+    # a device id that does not exist: folded onto the devices present by default (standalone ph4 passes an
+    # uninitialised gpu_id, jdata.h:137-170), the reference's -1 (sapporo.cpp:31-34) with G6_B200_STRICT_DEVICE=1
+    os.environ["G6_B200_STRICT_DEVICE"] = "1"
+    try:
+        assert g6.L.g6_open_(C.byref(C.c_int(4096))) == -1
+    finally:
+        del os.environ["G6_B200_STRICT_DEVICE"]
+    assert g6.L.g6_open_(C.byref(C.c_int(4096))) == 0 and g6.L.g6x_device_count_open() == 1
+    g6.close()
+    assert g6.L.g6_open_(C.byref(g6.cid)) == 0
 
 
 def test_full_size_n1m_sampled_oracle_and_properties(g6):
@@ -452,8 +464,10 @@ def test_device_resident_entry_point_matches_abi(g6):
                           d_sum.data_ptr(), d_key.data_ptr(), d_nn.data_ptr())
         torch.cuda.synchronize()
         s = d_sum.cpu().numpy()
-        assert np.array_equal(s[:, 0:3], out["acc"]) and np.array_equal(s[:, 3:6], out["jerk"])
-        assert np.array_equal(-s[:, 6], out["pot"]) and np.array_equal(d_nn.cpu().numpy(), out["nn"])
+        # same kernels, same j; the second call finds every particle's nearest-neighbour distance refreshed by the
+        # first, so a few more or fewer pairs take the FP64 path: equal to FP32 pair rounding, not bit for bit
+        check_forces(dict(acc=s[:, 0:3], jerk=s[:, 3:6], pot=-s[:, 6]), out, tol=3e-7, what="device entry vs ABI")
+        assert np.array_equal(d_nn.cpu().numpy(), out["nn"])
         # key = (float bits of r2min) << 32 | address
         key = d_key.cpu().numpy().astype(np.uint64)
         addr = (key & np.uint64(0xffffffff)).astype(np.int64)
