@@ -1736,20 +1736,20 @@ long long g6x_order_rebuilds(void) { return g_ctx[0].order_rebuilds; }
 
 // (warp x group) blocks the speculative kernel took FAR / NEAR / CLOSE and NEAR blocks it redid, since the last
 // call (device 0).  Counted only by builds with -DG6_STATS (returns 0 there, -1 otherwise).
-int g6x_block_stats(unsigned long long out[4])
+int g6x_block_stats(unsigned long long out[8])
 {
     require_open("g6x_block_stats");
-    for (int m = 0; m < 4; m++) out[m] = 0;
+    for (int m = 0; m < 8; m++) out[m] = 0;
 #ifdef G6_STATS
     use(0);
     CK(cudaStreamSynchronize(G.stream));
     if (!G.d_stats) {
-        dev_alloc(G.d_stats, 4);
-        CK(cudaMemset(G.d_stats, 0, 4 * sizeof(unsigned long long)));
+        dev_alloc(G.d_stats, 8);
+        CK(cudaMemset(G.d_stats, 0, 8 * sizeof(unsigned long long)));
         return 0;
     }
-    CK(cudaMemcpy(out, G.d_stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-    CK(cudaMemset(G.d_stats, 0, 4 * sizeof(unsigned long long)));
+    CK(cudaMemcpy(out, G.d_stats, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    CK(cudaMemset(G.d_stats, 0, 8 * sizeof(unsigned long long)));
     return 0;
 #else
     return -1;

@@ -949,10 +949,11 @@ __global__ void __launch_bounds__(THREADS, MINB) force_kernel(const __grid_const
 
     // ---- j tiles of this split -------------------------------------------
     const int ntiles_total = (p.nj + TILE - 1) / TILE;
-    const int tile0 = blockIdx.x * p.tiles_per_split;
-    int ntiles = ntiles_total - tile0;
-    if (ntiles > p.tiles_per_split) ntiles = p.tiles_per_split;
-    if (ntiles < 0) ntiles = 0;
+    // split s takes tiles s, s + nsplit, s + 2 nsplit, ...: the tiles that hold an i-block's own neighbourhood
+    // (FP64 pairs, masked blocks) are dealt out over all splits instead of landing on one CTA
+    const int tstride = p.nsplit;
+    int ntiles = ((int)blockIdx.x < ntiles_total) ? (ntiles_total - (int)blockIdx.x + tstride - 1) / tstride : 0;
+    auto tile_of = [&](const int t) -> int { return (int)blockIdx.x + t * tstride; };
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; s++) mbar_init(&sm.full[s], 1);
@@ -963,7 +964,7 @@ __global__ void __launch_bounds__(THREADS, MINB) force_kernel(const __grid_const
     constexpr uint32_t STAGE_BYTES = 3u * TILE * sizeof(float4);
     if (tid == 0) {
         for (int s = 0; s < STAGES && s < ntiles; s++) {
-            size_t off = (size_t)(tile0 + s) * TILE;
+            size_t off = (size_t)tile_of(s) * TILE;
             mbar_expect_tx(&sm.full[s], STAGE_BYTES);
             bulk_g2s(sm.A[s], p.jA + off, TILE * sizeof(float4), &sm.full[s]);
             bulk_g2s(sm.B[s], p.jB + off, TILE * sizeof(float4), &sm.full[s]);
@@ -1064,7 +1065,7 @@ __global__ void __launch_bounds__(THREADS, MINB) force_kernel(const __grid_const
         const uint32_t phase = (uint32_t)(t / STAGES) & 1u;
         while (!mbar_try_wait(&sm.full[s], phase)) {
         }
-        const int jtile = (tile0 + t) * TILE;
+        const int jtile = tile_of(t) * TILE;
         int cnt = p.nj - jtile;
         if (cnt > TILE) cnt = TILE;
         const float4 *tA = sm.A[s], *tB = sm.B[s], *tC = sm.C[s];
@@ -1146,7 +1147,7 @@ __global__ void __launch_bounds__(THREADS, MINB) force_kernel(const __grid_const
 
         __syncthreads();  // everyone is done with stage s
         if (tid == 0 && t + STAGES < ntiles) {
-            size_t off = (size_t)(tile0 + t + STAGES) * TILE;
+            size_t off = (size_t)tile_of(t + STAGES) * TILE;
             mbar_expect_tx(&sm.full[s], STAGE_BYTES);
             bulk_g2s(sm.A[s], p.jA + off, TILE * sizeof(float4), &sm.full[s]);
             bulk_g2s(sm.B[s], p.jB + off, TILE * sizeof(float4), &sm.full[s]);
@@ -1440,10 +1441,11 @@ __global__ void __launch_bounds__(THREADS, MINB) force_fast_kernel(const __grid_
     const int tid = threadIdx.x;
 
     const int ntiles_total = (p.nj + TILE - 1) / TILE;
-    const int tile0 = blockIdx.x * p.tiles_per_split;
-    int ntiles = ntiles_total - tile0;
-    if (ntiles > p.tiles_per_split) ntiles = p.tiles_per_split;
-    if (ntiles < 0) ntiles = 0;
+    // split s takes tiles s, s + nsplit, s + 2 nsplit, ...: the tiles that hold an i-block's own neighbourhood
+    // (FP64 pairs, masked blocks) are dealt out over all splits instead of landing on one CTA
+    const int tstride = p.nsplit;
+    int ntiles = ((int)blockIdx.x < ntiles_total) ? (ntiles_total - (int)blockIdx.x + tstride - 1) / tstride : 0;
+    auto tile_of = [&](const int t) -> int { return (int)blockIdx.x + t * tstride; };
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; s++) mbar_init(&sm.full[s], 1);
@@ -1460,7 +1462,7 @@ __global__ void __launch_bounds__(THREADS, MINB) force_fast_kernel(const __grid_
         bulk_g2s(sm.G[s], p.jG + (size_t)tile * TBOX, TBOX * sizeof(float4), &sm.full[s]);
     };
     if (tid == 0)
-        for (int s = 0; s < STAGES && s < ntiles; s++) issue_stage(s, tile0 + s);
+        for (int s = 0; s < STAGES && s < ntiles; s++) issue_stage(s, tile_of(s));
 
     // ---- register-resident i-pairs: i = block base + IPT*tid + k (consecutive = Morton neighbours) --------
     IPair IP[NP];
@@ -1548,7 +1550,7 @@ __global__ void __launch_bounds__(THREADS, MINB) force_fast_kernel(const __grid_
         const uint32_t phase = (uint32_t)(t / STAGES) & 1u;
         while (!mbar_try_wait(&sm.full[s], phase)) {
         }
-        const int jtile = (tile0 + t) * TILE;
+        const int jtile = tile_of(t) * TILE;
         int cnt = p.nj - jtile;
         if (cnt > TILE) cnt = TILE;
         const float4 *tA = sm.A[s], *tB = sm.B[s], *tC = sm.C[s], *tG = sm.G[s];
@@ -1560,7 +1562,7 @@ __global__ void __launch_bounds__(THREADS, MINB) force_fast_kernel(const __grid_
             const float sc = fmaxf(wsc, lo.w);
             bool hit = false;
 #pragma unroll
-            for (int k = 0; k < IPT; k++) hit |= ((cgrp[k] >> 3) == tile0 + t) & (cgrp[k] >= 0);
+            for (int k = 0; k < IPT; k++) hit |= ((cgrp[k] >> 3) == tile_of(t)) & (cgrp[k] >= 0);
             tile_far = (box_gap2(lo, hi) > fmaxf(farlim, p.ord.farc2 * sc * sc)) && !__any_sync(0xffffffffu, hit);
         }
 
@@ -1681,6 +1683,12 @@ __global__ void __launch_bounds__(THREADS, MINB) force_fast_kernel(const __grid_
                     unsigned int base = 0u;
                     if (lane == 0) base = atomicAdd(p.wl_count, (unsigned)total);
                     base = __shfl_sync(0xffffffffu, base, 0);
+#ifdef G6_STATS
+                    if (lane == 0 && p.stats) {
+                        atomicAdd(&p.stats[4], (unsigned long long)total);
+                        if (base + (unsigned)total > p.wl_cap) atomicAdd(&p.stats[5], 1ull);
+                    }
+#endif
                     unsigned int pos = base + (unsigned)(incl - mine);
 #pragma unroll
                     for (int k = 0; k < IPT; k++) {
@@ -1725,7 +1733,7 @@ __global__ void __launch_bounds__(THREADS, MINB) force_fast_kernel(const __grid_
         }
 
         __syncthreads();  // everyone is done with stage s
-        if (tid == 0 && t + STAGES < ntiles) issue_stage(s, tile0 + t + STAGES);
+        if (tid == 0 && t + STAGES < ntiles) issue_stage(s, tile_of(t + STAGES));
     }
 
 #ifdef G6_STATS

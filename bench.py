@@ -53,6 +53,11 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--shuffle-ids", action="store_true", help="ids permuted against the addresses")
+    ap.add_argument("--parity-sample", type=int, default=1024,
+                    help="i-particles checked against the oracle after the timed region (0: skip)")
+    ap.add_argument("--no-extras", dest="extras", action="store_false",
+                    help="skip the block-step latency table and the bounded ph4 run (N=1 only)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N>1: combine the j-shard partials inside the library over peer memory (default) or with "
                          "three NCCL all-reduces (the reference implementation of the exchange)")
@@ -85,10 +90,12 @@ def cpu_rate(mass, pos, vel, eps2, ni_total, procs):
     n = len(mass)
     per = max(1, ni_total // procs)
     jobs = [(kind, mass, pos, vel, eps2, k * per, (k + 1) * per) for k in range(procs)]
+    if kind == "reference":
+        O.ref()          # dlopen oracle/_ref/libph4ref.so in THIS process too, so the loaded-library record shows it
     if procs == 1:
         secs = [_cpu_worker(jobs[0])]
     else:
-        with mp.get_context("fork").Pool(procs) as pool:
+        with mp.get_context("spawn").Pool(procs) as pool:
             secs = pool.map(_cpu_worker, jobs)
     dt = max(secs)
     return per * procs * float(n) / dt, kind, per * procs, dt
@@ -123,7 +130,8 @@ def run_reference(a):
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "full i-block Hermite force sweep (acc, jerk, pot, nearest neighbour), "
                                "Plummer N=%d, eps2=%g; reference CPU loop on a bounded i-sample per step" % (n, a.eps2),
-                   "n": n, "eps2": a.eps2, "sample_i_per_step": ni},
+                   "n": n, "eps2": a.eps2, "sample_i_per_step": ni, "sample_fraction_of_sweep": ni / float(n),
+                   "host_cores": cores},
         "cpu_baseline": {"value": value, "unit": "interactions/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "interactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -181,6 +189,58 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def _sample_errors(acc, jerk, pot, nn, ref, ids):
+    """Per-particle relative errors of a sampled i-set against the oracle (north-star metric)."""
+    ea = np.linalg.norm(acc - ref["acc"], axis=1) / np.linalg.norm(ref["acc"], axis=1)
+    ej = np.linalg.norm(jerk - ref["jerk"], axis=1) / np.linalg.norm(ref["jerk"], axis=1)
+    ep = np.abs(pot - ref["pot"]) / np.abs(ref["pot"])
+    return {"acc": float(ea.max()), "jerk": float(ej.max()), "pot": float(ep.max()),
+            "nn_exact": float(np.mean(nn == ids[ref["nn"]]))}
+
+
+def _extras(a, n_dev):
+    """Driver-timed numbers of the other BASELINE configs (rank 0, N=1): block-step latency through the C ABI
+    (oracle/g6_latency: a C caller, no Python in the loop) and the unmodified reference ph4 (oracle/_ref/libph4ref_gpu.so,
+    its -DGPU objects linked to this library) at N=16k over a bounded interval, seconds per N-body time unit."""
+    out = {}
+    lib = os.path.join(ROOT, "amuse_b200", "csrc", "libsapporo.so")
+    lat = os.path.join(ROOT, "oracle", "g6_latency")
+    if os.path.exists(lat):
+        table = {}
+        for n in (16384, 131072):
+            try:
+                r = subprocess.run([lat, lib, str(n), "100"], capture_output=True, text=True, timeout=120)
+                rows = {}
+                for ln in r.stdout.splitlines():
+                    f = ln.replace("|", " ").replace(":", " ").split()
+                    if len(f) >= 4 and f[0] == "ni":
+                        rows[f[1]] = {"force_call_us": float(f[2]), "with_j_updates_us": float(f[3])}
+                table["N=%d" % n] = rows
+            except Exception as e:  # harness missing or failed: report, do not fail the bench
+                table["N=%d" % n] = repr(e)
+        out["block_step_latency"] = {"what": "us per block step through the g6 C ABI (ni j-updates, set_ti, firsthalf, "
+                                             "lasthalf2), C caller oracle/g6_latency.cc, uniform sphere, eps2=1e-4",
+                                     "table": table}
+    ref_gpu = os.path.join(ROOT, "oracle", "_ref", "libph4ref_gpu.so")
+    if os.path.exists(ref_gpu):
+        code = ("import sys, json; sys.path.insert(0, %r); from oracle import oracle as O; from amuse_b200 import plummer as P; "
+                "m, x, v = P.new_plummer_model(16384, seed=1); "
+                "r = O.ref_evolve(m, x, v, 0.0, 0.14, 0.0625, use_gpu=1, libname='libph4ref_gpu.so'); "
+                "print('RESULT ' + json.dumps(r))") % ROOT
+        try:
+            r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+            line = [l for l in r.stdout.splitlines() if l.startswith("RESULT ")]
+            d = json.loads(line[-1][7:])
+            out["ph4_s_per_unit"] = {"value": d["seconds"] / d["t"], "unit": "wall s per N-body time unit",
+                                     "config": "unmodified ph4 (oracle/_ref/libph4ref_gpu.so) through the g6 ABI, Plummer "
+                                               "N=16384, eps2=0, eta=0.14, t=0..%g" % d["t"],
+                                     "block_steps": d["block_steps"], "particle_steps": d["particle_steps"],
+                                     "dE_over_E": abs((d["E1"] - d["E0"]) / d["E0"])}
+        except Exception as e:
+            out["ph4_s_per_unit"] = {"value": None, "error": repr(e)}
+    return out
+
+
 def run_b200(a):
     import torch
     import torch.distributed as dist
@@ -202,8 +262,11 @@ def run_b200(a):
     n = a.n
     mass, pos, vel = P.new_plummer_model(n, seed=a.seed)      # identical on every rank
     ids = np.arange(1, n + 1, dtype=np.int32)
+    if a.shuffle_ids:      # ids unrelated to the addresses (a caller that does not load in id order)
+        ids = (np.random.RandomState(11).permutation(n) + 1).astype(np.int32)
     # j-domain of this rank: jdata::define_domain (src/amuse_ph4/src/jdata.cc:56-67)
     j0, j1 = S.define_domain(n, world, rank)
+    os.environ.pop("G6_B200_DEVICES", None)
     g = g6lib.G6(local)
     L = g.L
     L.g6x_set_stream(C.c_void_p(torch.cuda.current_stream(dev).cuda_stream), 1)
@@ -226,8 +289,6 @@ def run_b200(a):
     d_sum = torch.empty((n, 7), dtype=torch.float64, device=dev)
     d_key = torch.empty(n, dtype=torch.int64, device=dev)
     d_nn = torch.empty(n, dtype=torch.int32, device=dev)
-    h_sum = torch.empty((n, 7), dtype=torch.float64).pin_memory()
-    h_nn = torch.empty(n, dtype=torch.int32).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
     chunk_events = []
@@ -236,22 +297,23 @@ def run_b200(a):
         L.g6x_resolve_nn(n, keys.data_ptr(), rank, d_nn.data_ptr())
         return d_nn
 
-    def sweep(t, record=False):
+    def sweep(t, record=False, exchange=None):
         """predict + force sweep + cross-rank reduction; everything on the current stream."""
+        exchange = exchange or a.exchange
         L.g6x_predict(njl, float(t))
         if record:
             e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
             e0.record()
-        # one call for the whole i-set: the library cuts it into launches of `dchunk` i-particles
-        # idata.cc:284-313 on the device (sum, min key, id of the winner): either fused into the force
-        # kernels (stores into the peers' exchange buffers over NVLink + one combine kernel) ...
-        calc = L.g6x_calc_device_allreduce if (world > 1 and a.exchange == "peer") else L.g6x_calc_device
+        # one call for the whole i-set: the library sorts it (Morton), cuts it into launches of `dchunk` i-particles
+        # and combines the j-shards like idata.cc:284-313 on the device (sum, min key, id of the winner): either
+        # fused into the force kernels (stores into the peers' exchange buffers over NVLink + one combine kernel) ...
+        calc = L.g6x_calc_device_allreduce if (world > 1 and exchange == "peer") else L.g6x_calc_device
         calc(njl, n, d_id.data_ptr(), d_x.data_ptr(), d_v.data_ptr(), None, a.eps2, 1,
              d_sum.data_ptr(), d_key.data_ptr(), d_nn.data_ptr())
         if record:
             e1.record()
             chunk_events.append((e0, e1, n))
-        if world > 1 and a.exchange == "nccl":      # ... or as three NCCL all-reduces
+        if world > 1 and exchange == "nccl":      # ... or as three NCCL all-reduces
             S.combine_partials(d_sum, d_key, resolve)
 
     def barrier():
@@ -259,7 +321,9 @@ def run_b200(a):
             dist.barrier()
         torch.cuda.synchronize()
 
-    tstep = 2.0 ** -20            # a new time every step, so the predictor really runs each sweep
+    # a new time every step, so the predictor really runs each sweep; the particles carry no acc/jerk and the step is
+    # 2^-40, so positions move by < 1e-12 and the parity sample below still compares against the t = 0 oracle
+    tstep = 2.0 ** -40
     for w in range(a.warmup):
         flush.fill_(w)
         sweep(tstep * (w + 1))
@@ -291,17 +355,42 @@ def run_b200(a):
     ms_per_step = ms_total / a.steps
     value = float(n) * float(n) / (ms_per_step * 1e-3)
 
-    # roofline of the dominant kernel (force_kernel): per-launch algorithmic flop / mean launch duration
-    # (events bracket the force launches of one sweep; the predictor is outside them)
+    # roofline of the dominant kernel (force_fast_kernel): per-launch algorithmic flop / mean launch duration
+    # (events bracket the force launches of one sweep: Morton sort of the i-set, packing, neighbour-bound pre-pass,
+    # force kernel, FP64 pair kernel and partial reduction; the predictor is outside them)
     kms = np.array([e0.elapsed_time(e1) for e0, e1, _ in chunk_events]) / n_launch
     flop_per_launch = FLOP_PER_INTERACTION * (float(n) / n_launch) * njl
     achieved = flop_per_launch / (kms.mean() * 1e-3) / 1e12
     kernel_share = float(kms.sum() * n_launch / ms_total)
 
+    # ---- parity of what was just timed: a sampled i-set against the oracle (rank 0) ------------------------
+    parity = None
+    ref = None
+    samp = np.sort(np.random.RandomState(5).choice(n, min(a.parity_sample, n), replace=False))
+    if rank == 0 and a.parity_sample > 0:
+        from oracle import oracle as O
+        ref = O.force(pos[samp], vel[samp], mass, pos, vel, a.eps2, iid=ids[samp], jid=ids)
+    torch.cuda.synchronize()
+    if rank == 0 and ref is not None:
+        sel = torch.from_numpy(samp).to(dev)
+        s = d_sum[sel].cpu().numpy()
+        parity = {"tol": 1e-6, "sample_i": int(len(samp)), "checker": "oracle/ (FP64 restatement of idata.cc:198-236)",
+                  "device_path": _sample_errors(s[:, 0:3], s[:, 3:6], -s[:, 6], d_nn[sel].cpu().numpy(), ref, ids)}
+    if world > 1 and a.exchange == "peer" and a.parity_sample > 0:
+        # the same sweep with the exchange done by NCCL (three all-reduces): the fused exchange must agree
+        keep = d_sum.clone()
+        sweep(tstep * (a.warmup + a.steps + 1), exchange="nccl")
+        torch.cuda.synchronize()
+        if rank == 0:
+            sel = torch.from_numpy(samp).to(dev)
+            da = (keep[sel] - d_sum[sel]).abs().max(dim=0).values / d_sum[sel].abs().max(dim=0).values
+            parity["fused_vs_nccl_exchange_max_rel_diff"] = float(da.max().item())
+        del keep
+
     # measured FP32 FMA pipe peak (dependent-chain FFMA / FFMA2 microbenchmarks in the library)
     ffma = L.g6x_fp32_peak(0)
     ffma2 = L.g6x_fp32_peak(1)
-    # predictor: HBM-bound kernel, 112 B read + 48 B written per j
+    # predictor: HBM-bound kernel, 120 B read + 65 B written per j; L2 flushed between the timed launches
     pred_ms = L.g6x_time_predictor(njl, 20)
     pred_gbs = 185.0 * njl / (pred_ms * 1e-3) / 1e9 if pred_ms > 0 else None
 
@@ -315,48 +404,47 @@ def run_b200(a):
     tj1 = time.perf_counter()
     j_update = {"value": njl / (tj1 - tj0), "unit": "particles/s", "bytes_per_particle": 128,
                 "gbs": 128.0 * njl / (tj1 - tj0) / 1e9, "ms": 1e3 * (tj1 - tj0),
-                "bound": "host staging loop + PCIe (8192-record batches uploaded while the rest is staged)"}
+                "bound": "host staging loop + PCIe (8192-record batches uploaded while the rest is staged) + Morton "
+                         "re-ordering of the j-memory (a reload of everything makes the order stale)"}
 
-    # ---- end-to-end through the public API with host buffers ------------------------------------
+    # ---- end-to-end through the reference-facing API: the g6 C ABI with HOST arrays -------------------------
+    # N = 1: this process' library instance.  N > 1: ONE process (rank 0) opens all N devices behind the same ABI
+    # (G6_B200_DEVICES: j dealt out over the devices, partials gathered over peer memory) -- what a ph4 worker that
+    # links the library gets; the other ranks release their devices and wait.
     e2e = None
     if not a.no_e2e:
         e2e_steps = max(1, min(a.steps, 2))
-        if world == 1:
-            L.g6x_set_stream(None, 0)
-            g.set_ti(0.0)
-            g.calc(ids[:npipes], pos[:npipes], vel[:npipes], a.eps2)      # warm the ABI path
-            torch.cuda.synchronize()
+        g.close()
+        barrier()
+        how = None
+        if rank == 0:
+            if world > 1:
+                os.environ["G6_B200_DEVICES"] = str(world)
+            g2 = g6lib.G6(0)
+            g2.set_j_particles(ids, mass, pos, vel)
+            g2.set_ti(0.0)
+            g2.calc(ids[:npipes], pos[:npipes], vel[:npipes], a.eps2)      # warm the ABI path (and order the j-memory)
+            g2.synchronize()
             t0 = time.perf_counter()
             for k in range(e2e_steps):
-                g.set_ti(tstep * (100 + k))
-                out = g.calc(ids, pos, vel, a.eps2)
-            torch.cuda.synchronize()
+                g2.set_ti(tstep * (100 + k))
+                out = g2.calc(ids, pos, vel, a.eps2)
             dt = (time.perf_counter() - t0) / e2e_steps
-            h2d, d2h = 48 * n, 60 * n
-            how = "g6 C ABI, host double arrays, %d-particle chunks" % npipes
-        else:
-            def e2e_step(k=[100]):
-                k[0] += 1
-                d_id.copy_(h_id, non_blocking=True)
-                d_x.copy_(h_x, non_blocking=True)
-                d_v.copy_(h_v, non_blocking=True)
-                sweep(tstep * k[0])
-                h_sum.copy_(d_sum, non_blocking=True)
-                h_nn.copy_(d_nn, non_blocking=True)
-            e2e_step()
-            barrier()
-            t0 = time.perf_counter()
-            for _ in range(e2e_steps):
-                e2e_step()
-            barrier()
-            dt_t = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=dev)
-            dist.all_reduce(dt_t, op=dist.ReduceOp.MAX)
-            dt = float(dt_t.item())
-            h2d, d2h = (4 + 48) * n, 60 * n
-            how = "pinned host i-arrays -> H2D -> g6x_calc_device%s -> D2H, per rank" % (
-                "_allreduce (peer-memory exchange)" if a.exchange == "peer" else " -> 3 NCCL all-reduces")
-        e2e = {"value": float(n) * float(n) / dt, "unit": "interactions/s", "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "ms_per_step": dt * 1e3, "how": how}
+            if parity is not None:
+                parity["abi_e2e"] = _sample_errors(out["acc"][samp], out["jerk"][samp], out["pot"][samp], out["nn"][samp],
+                                                   ref, ids)
+            h2d, d2h = 64 * n * world, 60 * n
+            how = "g6 C ABI (g6_set_ti_, g6calc_firsthalf_/g6calc_lasthalf2_), host double arrays, %d-particle chunks" % npipes
+            if world > 1:
+                how += ", ONE process driving %d devices (G6_B200_DEVICES=%d)" % (world, world)
+            e2e = {"value": float(n) * float(n) / dt, "unit": "interactions/s", "h2d_bytes_per_step": h2d,
+                   "d2h_bytes_per_step": d2h, "ms_per_step": dt * 1e3, "how": how}
+            g2.close()
+            os.environ.pop("G6_B200_DEVICES", None)
+        if world > 1:
+            dist.barrier()
+    else:
+        g.close()
 
     # ---- CPU baseline on this box's host cores (rank 0, N=1 only) -------------------------------
     cpu = None
@@ -370,26 +458,40 @@ def run_b200(a):
         except Exception as e:  # the checker is optional infrastructure; never the measured path
             cpu = {"value": None, "unit": "interactions/s", "cores": 0, "kind": "unavailable", "sample": repr(e)}
 
-    g.close()
+    extras = _extras(a, world) if (rank == 0 and world == 1 and a.extras) else {}
+
+    ok = True
     if rank == 0:
+        if parity is not None:
+            for leg in ("device_path", "abi_e2e"):
+                if leg in parity:
+                    e = parity[leg]
+                    parity[leg]["ok"] = bool(e["acc"] <= 1e-6 and e["jerk"] <= 1e-6 and e["pot"] <= 1e-6 and e["nn_exact"] >= 0.999)
+                    ok = ok and parity[leg]["ok"]
+            if "fused_vs_nccl_exchange_max_rel_diff" in parity:
+                ok = ok and parity["fused_vs_nccl_exchange_max_rel_diff"] < 1e-9
+            parity["ok"] = bool(ok)
         peak_src = "nominal 148 SM x 128 lanes x 2 x 1.965 GHz (MEASURED_PEAKS.json holds no FP32 figure); " \
                    "measured FFMA microbenchmark alongside"
         line = {
             "metric": "interactions/s", "value": value, "unit": "interactions/s", "n_gpus": world,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f32 (double-single positions, f64 reduction)",
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32 (double-single positions, f64 reduction, f64 close pairs)",
             "data": "synthetic",
             "config": {"workload": "full i-block Hermite force sweep (acc, jerk, pot, nearest neighbour), "
                                    "Plummer N=%d, eps2=%g, %d i-particles per launch, j sharded over %d GPU(s)" % (
                                        n, a.eps2, dchunk, world),
                        "n": n, "eps2": a.eps2, "npipes": npipes, "i_per_launch": dchunk, "l2": "256 MiB buffer written between timed steps",
+                       "ids": "shuffled against the addresses" if a.shuffle_ids else "1..N in address order",
                        "parallelism": "j-shard x%d + %s" % (world, "none" if world == 1 else (
                            "peer-memory exchange fused into the force kernels (NVLink stores + combine kernel)"
                            if a.exchange == "peer" else "3 NCCL all-reduces"))},
             "tflops_60": value * FLOP_PER_INTERACTION / 1e12,
             "frac_fp32_peak_nominal": value * FLOP_PER_INTERACTION / 1e12 / (NOMINAL_FP32_TFLOPS * world),
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": NOMINAL_FP32_TFLOPS, "unit": "TFLOP/s",
-                         "frac": achieved / NOMINAL_FP32_TFLOPS, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / NOMINAL_FP32_TFLOPS, "traffic": None,
+                         "traffic_note": "not measured in the run (DRAM bytes need ncu); profiles/ holds the ncu capture",
+                         "peak_source": peak_src,
                          "kernel": "force_fast_kernel", "flop_per_launch": flop_per_launch,
                          "ms_per_launch": float(kms.mean()), "launches_timed": int(len(kms) * n_launch),
                          "kernel_share_of_step": kernel_share,
@@ -398,15 +500,9 @@ def run_b200(a):
             "predictor": {"bound": "hbm", "achieved": pred_gbs, "unit": "GB/s", "bytes_per_j": 185,
                           "ms_per_launch": pred_ms},
             "j_update": j_update,
-            "e2e": e2e, "cpu_baseline": cpu, "gpu_launches": int(launches), "clocks": clocks,
+            "e2e": e2e, "cpu_baseline": cpu, "parity": parity, "gpu_launches": int(launches), "clocks": clocks,
         }
-        try:   # DRAM bytes of one force launch from the committed ncu capture of this very shape
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_force_traffic.json")))
-            if tr["n"] == n and world == 1:
-                line["roofline"]["traffic"] = tr["dram_bytes_read"] + tr["dram_bytes_write"]
-                line["roofline"]["traffic_unit"] = "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)"
-        except Exception:
-            pass
+        line.update(extras)
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
             if pred_gbs:
@@ -417,6 +513,8 @@ def run_b200(a):
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+    if not ok:
+        raise SystemExit("bench.py: parity check failed (see the 'parity' block of the line above)")
 
 
 if __name__ == "__main__":

@@ -157,7 +157,7 @@ long long g6x_order_rebuilds(void);
 /* Diagnostics of the pair classification: (warp of i) x (group of j) blocks taken FAR / NEAR / CLOSE and NEAR
  * blocks redone exactly, since the previous call.  Only builds with -DG6_STATS count (returns 0; the first
  * call arms the counters); the production build returns -1. */
-int g6x_block_stats(unsigned long long out[4]);
+int g6x_block_stats(unsigned long long out[8]);   /* [4] = FP64 pairs queued, [5] = appends that met a full list */
 /* Devices g6_open_ opened (G6_B200_DEVICES; 0 when closed). */
 int g6x_device_count_open(void);
 /* This process owns j-addresses whose GLOBAL address is local + offset (used

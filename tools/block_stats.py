@@ -42,7 +42,7 @@ d_v = torch.from_numpy(v).to(dev)
 d_sum = torch.empty((n, 7), dtype=torch.float64, device=dev)
 d_key = torch.empty(n, dtype=torch.int64, device=dev)
 d_nn = torch.empty(n, dtype=torch.int32, device=dev)
-st = (C.c_ulonglong * 4)()
+st = (C.c_ulonglong * 8)()
 have_stats = L.g6x_block_stats(st) == 0
 from oracle import oracle as O  # noqa: E402
 rnd = np.random.RandomState(5)
@@ -62,8 +62,8 @@ def stats():
         return ""
     L.g6x_block_stats(st)
     tot = float(sum(st[:3])) or 1.0
-    return " | blocks FAR %.2f%% NEAR %.2f%% CLOSE %.3f%% (NEAR redone %.4f%%)" % (
-        100 * st[0] / tot, 100 * st[1] / tot, 100 * st[2] / tot, 100 * st[3] / tot)
+    return " | blocks FAR %.2f%% NEAR %.2f%% CLOSE %.3f%% (NEAR redone %.4f%%), FP64 pairs queued %d (%d appends met a full list)" % (
+        100 * st[0] / tot, 100 * st[1] / tot, 100 * st[2] / tot, 100 * st[3] / tot, st[4], st[5])
 
 
 tag = os.path.basename(os.environ.get("G6_B200_LIB", "libsapporo.so"))
