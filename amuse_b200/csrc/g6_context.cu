@@ -108,7 +108,7 @@ struct Context {
     bool ids_dirty = false;
     long long updates_since_order = 0, updates_since_force = 0;
     long long order_rebuilds = 0;
-    float kclose = 16.f;               // G6_B200_KCLOSE
+    float kclose = 32.f;               // G6_B200_KCLOSE
     float farc = 0.125f;               // G6_B200_FARC
     int near_w = 32;                   // Morton window (each side) of the neighbour-bound scans
     unsigned long long *d_stats = nullptr;   // block-class counters (-DG6_STATS builds)
@@ -232,6 +232,8 @@ struct Context {
     int cur_ni = 0, cur_nj = 0;
     float cur_eps2 = 0.f;
     bool cur_any_h2 = false;
+    bool cur_spread = false;   // the pending i-block went to all devices (multi-device mode)
+    cudaEvent_t i_ready = nullptr;   // root: the packed i-block has arrived in d_i
     bool pending = false;
 };
 
@@ -904,7 +906,7 @@ void launch_force(int nj, int ni, const IBlock &ib, float eps2, bool nn, bool li
     }
     if (v == V_F2 || v == V_F4) {
         // pre-pass of the speculative kernel: id-table lookup and nearest-neighbour bound of every i-particle
-        near_kernel<<<(ni + 255) / 256, 256, 0, G.stream>>>(a, G.near_w);
+        near_kernel<<<(ni + 7) / 8, 256, 0, G.stream>>>(a, G.near_w);   // one warp per particle
         CK(cudaGetLastError());
         G.launches++;
     }
@@ -1088,15 +1090,18 @@ int get_device_count(void)
 
 // ---- multi-device layer ----------------------------------------------------------------------------
 // G6_B200_DEVICES = n > 1 (or "all"): g6_open_ opens n devices in this one process and drives them as ONE
-// j-memory -- the device-side form of ph4's MPI mode (gpu.cc:40,56-59 + idata.cc:284-313) without MPI:
-// j-addresses are dealt out in chunks of 256 (address / 256 mod n owns it, so every device holds a uniform
-// sample of the system and any prefix [0, nj) is a prefix on every device), g6_set_j_particle_ goes to the
-// owner, g6calc_firsthalf_ sends the packed i-block to all devices and launches the force kernels, which
-// store their partial sums into device 0's exchange buffer over NVLink (peer access enabled directly), and
-// device 0 combines them (sum, min key, id of the winner) for g6calc_lasthalf_.
+// g6 device -- the device-side form of ph4's MPI mode (gpu.cc:40,56-59 + idata.cc:284-313) without MPI.
+// Like ph4's ranks, every device holds ALL particles (g6_set_j_particle_ goes to every device; 180 GB of HBM
+// hold tens of millions), so the Morton order of the j-memory is the same everywhere.  A big i-block is sent to
+// all devices, device k sums over its window of the SLOTS (contiguous tiles, ~1/n of the j each), the force
+// kernels store their partial sums into device 0's exchange buffer over NVLink (peer access enabled directly)
+// and device 0 combines them (sum, min key, id of the winner) for g6calc_lasthalf_.  A small i-block (the
+// block-timestep regime, where launch latency is everything) runs on device 0 alone, exactly like the one-device
+// library; the other devices keep their pending j-updates staged until they are needed.
 struct Multi {
     int n = 0;           // devices open (0: library closed)
     int dev_now = -1;    // device the CUDA runtime currently has selected
+    double spread_min = 1.0e8;   // G6_B200_SPREAD_MIN: ni x nj per device from which a block goes to all devices
 } M;
 
 static void use(int k)
@@ -1107,18 +1112,13 @@ static void use(int k)
         M.dev_now = G.device;
     }
 }
-static inline int owner_of(int address) { return M.n > 1 ? (address / TILE) % M.n : 0; }
-static inline int local_address(int address)
+// window of slots [lo, hi) device k sums over when a block is spread over nd devices (whole tiles)
+static inline void slot_window(int nj, int k, int nd, int &lo, int &hi)
 {
-    return M.n > 1 ? (address / (TILE * M.n)) * TILE + address % TILE : address;
-}
-// addresses of [0, nj) that device k owns form the prefix [0, local_count) of its local addresses
-static inline int local_count(int nj, int k)
-{
-    if (M.n <= 1) return nj;
-    const int cycle = TILE * M.n;
-    const int rem = nj % cycle - k * TILE;
-    return (nj / cycle) * TILE + std::max(0, std::min(TILE, rem));
+    const int ntiles = (nj + TILE - 1) / TILE;
+    const int per = (ntiles + nd - 1) / nd;
+    lo = std::min(nj, k * per * TILE);
+    hi = std::min(nj, (k + 1) * per * TILE);
 }
 
 static void open_context(int dev)   // g_cur selected by the caller
@@ -1143,7 +1143,7 @@ static void open_context(int dev)   // g_cur selected by the caller
     G.force_nsplit = env_int("G6_B200_NSPLIT", 0);
     {
         const char *e = getenv("G6_B200_KCLOSE");
-        G.kclose = (e && *e) ? (float)atof(e) : 16.f;
+        G.kclose = (e && *e) ? (float)atof(e) : 32.f;
         e = getenv("G6_B200_FARC");
         G.farc = (e && *e) ? (float)atof(e) : 0.125f;
         G.near_w = std::max(1, env_int("G6_B200_NEAR_WINDOW", 32));
@@ -1198,6 +1198,8 @@ static void close_context()
                 1e6 * G.tr[3] / G.tr_calls, 1e6 * G.tr[4] / G.tr_calls, 1e6 * G.tr[5] / G.tr_calls,
                 1e6 * G.tr[6] / G.tr_calls, 1e6 * G.tr[7] / G.tr_calls, G.order_rebuilds);
     free_all();
+    if (G.i_ready) cudaEventDestroy(G.i_ready);
+    G.i_ready = nullptr;
     if (G.own_stream) cudaStreamDestroy(G.own_stream);
     G.own_stream = G.stream = nullptr;
     G.open = false;
@@ -1241,6 +1243,10 @@ int g6_open_(int *id)
         open_context((dev + k) % ndev);
     }
     M.n = want;
+    {
+        const char *e = getenv("G6_B200_SPREAD_MIN");
+        M.spread_min = (e && *e) ? atof(e) : 1.0e8;
+    }
     if (want > 1) peer_group_setup();
     use(0);
     return 0;
@@ -1281,12 +1287,15 @@ int g6_set_j_particle_(int *cluster_id, int *address, int *index, double *tj, do
     (void)cluster_id; (void)dtj; (void)k18;
     require_open("g6_set_j_particle_");
     if (M.n > 1) {
-        if (*address < 0) {
-            fprintf(stderr, "g6_b200: FATAL g6_set_j_particle address %d < 0\n", *address);
-            exit(-1);
+        for (int k = 0; k < M.n; k++) {
+            g_cur = &g_ctx[k];
+            // (stage_j only touches the device when a buffer grows or a big batch is flushed early)
+            const bool touches = (*address + 1 > G.capacity) || (G.up_n + 1 > G.up_cap) ||
+                                 (G.eager_flush > 0 && G.up_n + 1 >= G.eager_flush);
+            if (touches) use(k);
+            stage_j(*address, *index, *tj, *mass, j6, a2, v, x);
         }
-        use(owner_of(*address));
-        stage_j(local_address(*address), *index, *tj, *mass, j6, a2, v, x, *address);
+        g_cur = &g_ctx[0];
         return 0;
     }
     stage_j(*address, *index, *tj, *mass, j6, a2, v, x);
@@ -1363,29 +1372,32 @@ void g6calc_firsthalf_(int *cluster_id, int *nj, int *ni, int index[], double xi
         }
     use(0);
     double t0 = G.trace ? wall() : 0.0, t1 = 0.0;
+    // a big block goes to all devices (each sums over its window of the slots), a small one to device 0 alone
+    const int njc = std::min(*nj, std::max(R.capacity, 0));
+    const bool spread = (nd > 1) && ((double)n * (double)njc >= M.spread_min * nd);
+    R.cur_spread = spread;
     // scatter (small batches: fused with the predictor, records read from mapped pinned memory) + predict;
-    // the Morton order of the j-memory is rebuilt first when a bulk load or new ids made it stale (all devices
-    // together: they share the origin the i-block is packed against)
-    bool stale = false;
+    // the Morton order of the j-memory is rebuilt first when a bulk load or new ids made it stale -- on ALL
+    // devices at once (same state in, same permutation out: the slot windows must mean the same particles
+    // everywhere), with device 0's origin
+    const bool stale = order_stale(*nj);
     for (int k = 0; k < nd; k++) {
-        g_cur = &g_ctx[k];
-        stale |= order_stale(local_count(*nj, k));
-    }
-    for (int k = 0; k < nd; k++) {
+        if (!stale && !spread && k > 0) break;
         use(k);
         if (stale) {
             flush_updates();
-            rebuild_order(local_count(*nj, k));
+            rebuild_order(*nj);
         }
-        predict_with_updates(local_count(*nj, k));
+        if (k == 0 || spread) predict_with_updates(*nj);
     }
     use(0);
     G6_TR(0)
     G6_TR(1)
     const bool inl = (n > 0) && (n <= G.inline_max) && (G.variant == V_AUTO);
     // Morton-sort the block when it goes to the speculative kernel (whose warps want 64 neighbouring particles)
-    const bool sorted = (n > 1) && is_fast_variant(choose_variant(n, std::min(local_count(*nj, 0), G.capacity))) &&
-                        G.ord.nkeys > 0;
+    int wlo = 0, whi = njc;
+    if (spread) slot_window(njc, 0, nd, wlo, whi);
+    const bool sorted = (n > 1) && is_fast_variant(choose_variant(n, whi - wlo)) && G.ord.nkeys > 0;
     if (sorted) host_morton_perm(n, xi); else G.h_perm.clear();
     // pack the i-block: double -> double-single relative to the origin (sapporo.cpp:125-134); the four
     // float4 streams are laid out back to back with stride n, so that they cross PCIe in ONE copy
@@ -1425,7 +1437,7 @@ void g6calc_firsthalf_(int *cluster_id, int *nj, int *ni, int index[], double xi
     // h2 = eps2 on every call (gpu.cc:266,324; gravity.F:72) and never read the lists, so they are
     // built on demand by g6_read_neighbour_list_.
     // outputs: [7n doubles][n ints] back to back, so that they come back in ONE copy
-    if (n > 0 && nd == 1) {
+    if (n > 0 && !spread) {
         if (!inl) CK(cudaMemcpyAsync(G.d_i, G.h_i, sizeof(float4) * 4 * (size_t)n, cudaMemcpyHostToDevice, G.stream));
         G6_TR(3)
         double *out = direct ? G.dev_h_sum : G.d_sum;
@@ -1433,18 +1445,31 @@ void g6calc_firsthalf_(int *cluster_id, int *nj, int *ni, int index[], double xi
                      reinterpret_cast<int *>(out + 7 * (size_t)n), inl ? G.h_i : nullptr,
                      direct ? ++G.flag_seq : 0ull);
     } else if (n > 0) {
-        // every device gets the block (from the root's pinned copy) and sums over its own j; the partials meet
-        // in the root's exchange buffer, where the root's combine kernel writes the totals (and raises the flag)
+        // every device gets the block (from the root's pinned copy) and sums over its window of the slots; the
+        // partials meet in the root's exchange buffer, where the root's combine kernel writes the totals (and
+        // raises the flag)
         gather_begin_all(n);
-        const unsigned long long seq = direct ? ++R.flag_seq : 0ull;
+        if (direct) ++R.flag_seq;
+        if (!inl) {   // the block crosses PCIe once (to the root) and reaches the other devices over NVLink
+            use(0);
+            CK(cudaMemcpyAsync(R.d_i, R.h_i, sizeof(float4) * 4 * (size_t)n, cudaMemcpyHostToDevice, R.stream));
+            if (!R.i_ready) CK(cudaEventCreateWithFlags(&R.i_ready, cudaEventDisableTiming));
+            CK(cudaEventRecord(R.i_ready, R.stream));
+        }
         for (int k = 0; k < nd; k++) {
             use(k);
-            if (!inl) CK(cudaMemcpyAsync(G.d_i, R.h_i, sizeof(float4) * 4 * (size_t)n, cudaMemcpyHostToDevice, G.stream));
-            gather_launch(k, local_count(*nj, k), n, iblock_of(G.d_i, n, G.d_conf), R.cur_eps2, nullptr, nullptr, nullptr,
+            if (!inl && k > 0) {
+                CK(cudaStreamWaitEvent(G.stream, R.i_ready, 0));
+                CK(cudaMemcpyPeerAsync(G.d_i, G.device, R.d_i, R.device, sizeof(float4) * 4 * (size_t)n, G.stream));
+            }
+            int lo, hi;
+            slot_window(njc, k, nd, lo, hi);
+            G.win_lo = lo;
+            gather_launch(k, hi - lo, n, iblock_of(G.d_i, n, G.d_conf), R.cur_eps2, nullptr, nullptr, nullptr,
                           inl ? R.h_i : nullptr, 0ull);
+            G.win_lo = 0;
             G.i_on_device = !inl;
         }
-        (void)seq;
         gather_finish_all(n, direct);
         use(0);
         G6_TR(3)
@@ -1544,12 +1569,17 @@ int g6_read_neighbour_list_(int *cluster_id)
         R.ngb_fetched = false;
         return 0;  // no lists were requested (all h2 <= 0 or lasthalf without nn)
     }
-    const int nd = std::max(1, M.n);
+    const int nd = R.cur_spread ? M.n : 1;   // devices that hold the i-block
     const int ni = R.cur_ni;
     if (!R.ngb_built) {
+        const int njc = std::min(R.cur_nj, std::max(R.capacity, 0));
         for (int k = 0; k < nd; k++) {
             use(k);
-            build_lists_here(local_count(R.cur_nj, k), ni, R.cur_eps2);
+            int lo = 0, hi = njc;
+            if (nd > 1) slot_window(njc, k, nd, lo, hi);
+            G.win_lo = lo;
+            build_lists_here(hi - lo, ni, R.cur_eps2);
+            G.win_lo = 0;
         }
         R.ngb_built = true;
     }
@@ -1594,7 +1624,7 @@ int g6_get_neighbour_list_(int *cluster_id, int *ipipe, int *maxlength, int *n_n
         *n_neighbours = 0;
         return 0;
     }
-    const int nd = std::max(1, M.n);
+    const int nd = R.cur_spread ? M.n : 1;
     const int pos = R.h_perm2[ip];
     static std::vector<int> merged;
     merged.clear();
@@ -1671,8 +1701,8 @@ int get_j_part_data(int addr, int nj, double *pos, double *vel, double *acc, dou
 {
     require_open("get_j_part_data");
     if (addr < 0 || addr >= nj) return -1;
-    use(owner_of(addr));
-    const int la = local_address(addr);
+    use(0);
+    const int la = addr;
     flush_updates();
     if (la >= G.capacity) {
         use(0);
@@ -1770,16 +1800,17 @@ int g6x_set_j_particles(int n, const int *address, int address0, const int *inde
     require_open("g6x_set_j_particles");
     static const double zero3[3] = {0, 0, 0};
     if (n <= 0) return 0;
-    if (M.n > 1) {   // one j-memory over several devices: every particle goes to its owner
-        for (int k = 0; k < n; k++) {
-            const int a = address ? address[k] : address0 + k;
-            if (a < 0) {
-                fprintf(stderr, "g6_b200: FATAL g6x_set_j_particles address %d < 0\n", a);
-                exit(-1);
-            }
-            use(owner_of(a));
-            stage_j(local_address(a), index[k], tj ? tj[k] : 0.0, mass[k], j6 ? j6[k] : zero3, a2 ? a2[k] : zero3, v[k],
-                    x[k], a);
+    if (M.n > 1) {   // every device holds all particles
+        for (int d = 0; d < M.n; d++) {
+            use(d);
+            int maxa = address0 + n - 1;
+            if (address)
+                for (int k = 0; k < n; k++) maxa = std::max(maxa, address[k]);
+            ensure_capacity(maxa + 1);
+            ensure_up_cap(G.up_n + n);
+            for (int k = 0; k < n; k++)
+                stage_j(address ? address[k] : address0 + k, index[k], tj ? tj[k] : 0.0, mass[k], j6 ? j6[k] : zero3,
+                        a2 ? a2[k] : zero3, v[k], x[k]);
         }
         use(0);
         return 0;
@@ -1803,8 +1834,8 @@ int g6x_predict(int nj, double ti)
         use(k);
         G.ti = ti;
         flush_updates();
-        if (order_stale(local_count(nj, k))) rebuild_order(local_count(nj, k));
-        run_predictor(local_count(nj, k));
+        if (order_stale(nj)) rebuild_order(nj);
+        run_predictor(nj);
     }
     use(0);
     return 0;

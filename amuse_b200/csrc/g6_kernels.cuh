@@ -1396,32 +1396,38 @@ __global__ void __launch_bounds__(256) close_pairs_kernel(const ForceArgs p)
     }
 }
 
-// Pre-pass of the speculative kernel, one thread per packed i-particle: the slot of the j-particle that
-// carries its id (conf[]) and a strict upper bound of its nearest-neighbour distance (iD.w) -- the
-// smallest distance to the 2W predicted j around its place in the Morton order.
+// Pre-pass of the speculative kernel, one WARP per packed i-particle (the lanes share the window, so the pass costs
+// two dependent loads whatever the window): the slot of the j-particle that carries its id (conf[]) and a
+// strict upper bound of its nearest-neighbour distance (iD.w) -- the smallest distance to the 2W predicted j
+// around its place in the Morton order.
 __global__ void __launch_bounds__(256) near_kernel(const ForceArgs p, const int W)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (i >= p.ni) return;
     const float4 a = p.iA[i], b = p.iB[i];
     const int iid = __float_as_int(b.w);
     const int self = hash_lookup(p.ord, iid);
-    p.conf[i] = self;
     float d2 = __int_as_float(0x7f800000);
     if (p.ord.nkeys > 0) {
         int s = self;
         if (s < 0 || s >= p.ord.nkeys) s = key_search(p.ord, morton30(a.x, a.y, a.z, p.ord.blo, p.ord.binv));
         const int lo = max(0, s - W), hi = min(p.ord.nkeys, s + W + 1);
-        for (int j = lo; j < hi; j++) {
+        for (int j = lo + lane; j < hi; j += 32) {
             const float4 ja = p.js.A[j], jb = p.js.B[j];
             const float dx = (ja.x - a.x) + (jb.x - b.x), dy = (ja.y - a.y) + (jb.y - b.y), dz = (ja.z - a.z) + (jb.z - b.z);
             const float r2 = dx * dx + dy * dy + dz * dz;
             if (ja.w > 0.f && __float_as_int(jb.w) != iid && r2 > TINYF) d2 = fminf(d2, r2);
         }
     }
-    float4 d = p.iD[i];
-    d.w = d2 * 1.0001f;   // the kernel's own r2 of that pair may round differently
-    const_cast<float4 *>(p.iD)[i] = d;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) d2 = fminf(d2, __shfl_xor_sync(0xffffffffu, d2, off));
+    if (lane == 0) {
+        p.conf[i] = self;
+        float4 d = p.iD[i];
+        d.w = d2 * 1.0001f;   // the kernel's own r2 of that pair may round differently
+        const_cast<float4 *>(p.iD)[i] = d;
+    }
 }
 
 template <int IPT, bool NN, bool NR, int MINB, bool EPS0>

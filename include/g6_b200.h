@@ -145,7 +145,7 @@ int g6x_set_stream(void *cuda_stream, int external);
 /* 1 (default): one Newton step on the reciprocal square root (per-pair error at
  * the FP32 rounding floor); 0: raw MUFU.RSQ (2^-22.9), ~10 % faster. */
 int g6x_set_refine(int on);
-/* Accuracy / speed parameters of the pair classification (defaults: G6_B200_KCLOSE = 16, G6_B200_FARC = 0.125):
+/* Accuracy / speed parameters of the pair classification (defaults: G6_B200_KCLOSE = 32, G6_B200_FARC = 0.125):
  * k_close: pairs closer than sqrt(k_close) x (the i-particle's nearest-neighbour distance) are evaluated
  * in FP64 with the reference's expression tree (0 switches that off: plain FP32 pair arithmetic);
  * far_factor: (warp of i) x (group of j) blocks whose bounding boxes are further apart than far_factor x
