@@ -1159,11 +1159,45 @@ __global__ void __launch_bounds__(THREADS, MINB) force_kernel(const __grid_const
     if (p.corr) {
         __syncthreads();
         const unsigned int nwl = sm.wl_n < (unsigned)CTA_WL ? sm.wl_n : (unsigned)CTA_WL;
-        for (unsigned int e = tid; e < nwl; e += THREADS) {
-            const int2 w = sm.wl[e];
-            const float4 ia = (INL > 0) ? ii.d[w.x] : p.iA[w.x], ib = (INL > 0) ? ii.d[INL + w.x] : p.iB[w.x],
-                         ic = (INL > 0) ? ii.d[2 * INL + w.x] : p.iC[w.x], id = (INL > 0) ? ii.d[3 * INL + w.x] : p.iD[w.x];
-            close_pair_to_corr(p, ia, ib, ic, id, w.x, w.y);
+        const unsigned int nround = (nwl + 31u) & ~31u;   // whole warps stay in the loop (shuffles below)
+        for (unsigned int e = tid; e < nround; e += THREADS) {
+            int wi = -1;
+            double v[7] = {0, 0, 0, 0, 0, 0, 0};
+            if (e < nwl) {
+                const int2 w = sm.wl[e];
+                wi = w.x;
+                const float4 ia = (INL > 0) ? ii.d[w.x] : p.iA[w.x], ib = (INL > 0) ? ii.d[INL + w.x] : p.iB[w.x],
+                             ic = (INL > 0) ? ii.d[2 * INL + w.x] : p.iC[w.x], id = (INL > 0) ? ii.d[3 * INL + w.x] : p.iD[w.x];
+                const float4 a = p.jA[w.y], b = p.jB[w.y], c = p.jC[w.y], l = p.jL[w.y];
+                fp64_accumulate(v, ((double)a.x + (double)b.x) - ((double)ia.x + (double)ib.x),
+                                ((double)a.y + (double)b.y) - ((double)ia.y + (double)ib.y),
+                                ((double)a.z + (double)b.z) - ((double)ia.z + (double)ib.z),
+                                ((double)c.x + (double)l.x) - ((double)ic.x + (double)id.x),
+                                ((double)c.y + (double)l.y) - ((double)ic.y + (double)id.y),
+                                ((double)c.z + (double)l.z) - ((double)ic.z + (double)id.z), (double)a.w + (double)l.w, eps2t);
+            }
+            // a CTA of a small block holds a handful of particles: sum the lanes of each particle with shuffles and
+            // let one lane add the seven totals (hundreds of pairs per particle would otherwise queue up on seven
+            // addresses); with many particles per warp the lanes add their own
+            unsigned int todo = __ballot_sync(0xffffffffu, wi >= 0);
+            for (int round = 0; round < 4 && todo; round++) {
+                const int cur = __shfl_sync(0xffffffffu, wi, __ffs(todo) - 1);
+                const bool mine = (wi == cur);
+                const unsigned int grp = __ballot_sync(0xffffffffu, mine);
+#pragma unroll
+                for (int q = 0; q < 7; q++) {
+                    double x = mine ? v[q] : 0.0;
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
+                    if ((int)(tid & 31) == __ffs(grp) - 1) atomicAdd(p.corr + (size_t)cur * 7 + q, x);
+                }
+                if (mine) wi = -1;
+                todo &= ~grp;
+            }
+            if (wi >= 0) {
+#pragma unroll
+                for (int q = 0; q < 7; q++) atomicAdd(p.corr + (size_t)wi * 7 + q, v[q]);
+            }
         }
         __threadfence();   // the atomics precede this CTA's ticket / final stores
     }

@@ -152,6 +152,21 @@ def ref(libname="libph4ref.so"):
     return _ref[libname]
 
 
+def ref_evolve_enc(mass, pos, vel, eps2, eta, t_end, manage_encounters=1, ids=None, use_gpu=True,
+                   libname="libph4ref_gpu.so", max_block_steps=0):
+    """The reference integrator with its own close-encounter management (ph4ref_evolve_enc in ref_driver.cc)."""
+    n = len(mass)
+    L = ref(libname)
+    out = np.zeros(8)
+    ids_ = _c(ids, np.int32) if ids is not None else None
+    L.ph4ref_evolve_enc.argtypes = [C.c_int, C.c_void_p, _dp, _dp, _dp, C.c_double, C.c_double, C.c_double, C.c_int,
+                                    C.c_int, C.c_long, _dp]
+    L.ph4ref_evolve_enc(n, ids_.ctypes.data if ids is not None else None, _c(mass), _c(pos), _c(vel), float(eps2),
+                        float(eta), float(t_end), int(use_gpu), int(manage_encounters), int(max_block_steps), out)
+    return dict(E0=out[0], E1=out[1], block_steps=int(out[2]), particle_steps=int(out[3]), seconds=out[4], t=out[5],
+                nj_left=int(out[6]))
+
+
 def ref_full_sweep(mass, pos, vel, eps2, ids=None):
     """Reference ph4 idata::setup() sweep (i = j, t = 0).  Returns dict + seconds."""
     n = len(mass)

@@ -272,4 +272,38 @@ int ph4ref_evolve_steps(int n, const int *id, const double *mass, const double *
     return 0;
 }
 
+// The same loop with ph4's own close-encounter management switched on, as its standalone driver runs it
+// (parallel_hermite_4.cc:185,215: set_manage_encounters(m) + advance_and_check_encounter(); m = 1 replaces a
+// close pair by its centre of mass with unperturbed two-body motion, close_encounter.cc:1-9,66-73).  BASELINE
+// configs[3]: without it the primordial binaries pin the time step.  out[6] = particles left in the j-memory.
+int ph4ref_evolve_enc(int n, const int *id, const double *mass, const double *pos, const double *vel, double eps2,
+                      double eta, double t_end, int use_gpu, int manage_encounters, long max_block_steps, double *out)
+{
+    quiet q;
+    jdata jd;
+    load(jd, n, id, mass, pos, vel, eps2, eta, use_gpu != 0);
+    jd.set_manage_encounters(manage_encounters);
+    jd.initialize_arrays();
+    idata id_(&jd);
+    jd.set_initial_timestep();
+    scheduler sched(&jd);
+    jd.E0 = jd.get_energy();
+    double t0 = wall();
+    long steps = 0;
+    while (jd.system_time < t_end && (max_block_steps <= 0 || steps < max_block_steps)) {
+        jd.advance_and_check_encounter();
+        steps++;
+    }
+    double t1 = wall();
+    jd.synchronize_all();
+    out[0] = jd.E0;
+    out[1] = jd.get_energy();
+    out[2] = jd.block_steps;
+    out[3] = jd.total_steps;
+    out[4] = t1 - t0;
+    out[5] = jd.system_time;
+    out[6] = jd.nj;
+    return 0;
+}
+
 }  // extern "C"
