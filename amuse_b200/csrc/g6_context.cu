@@ -118,7 +118,7 @@ struct Context {
     size_t wl_cap = 0;
     double *d_corr = nullptr;
     size_t corr_cap = 0;
-    int wl_per_i = 512;                // G6_B200_WL_PER_I: list entries reserved per i-particle of a launch
+    int wl_per_i = 1024;               // G6_B200_WL_PER_I: list entries reserved per i-particle of a launch
     double ti = 0.0;
     double predicted_ti = 0.0;
     int predicted_nj = -1;  // prefix predicted at predicted_ti (-1: none)
@@ -233,6 +233,7 @@ struct Context {
     float cur_eps2 = 0.f;
     bool cur_any_h2 = false;
     bool cur_spread = false;   // the pending i-block went to all devices (multi-device mode)
+    int cd_win_lo = 0, cd_win_hi = 0;   // g6x_set_j_window: slots the device-resident entry points sum over (hi == 0: all)
     cudaEvent_t i_ready = nullptr;   // root: the packed i-block has arrived in d_i
     bool pending = false;
 };
@@ -605,7 +606,7 @@ void ensure_close_buffers(size_t ni, bool with_list)
         dev_alloc(G.d_wl_count, 1);
         CK(cudaMemsetAsync(G.d_wl_count, 0, sizeof(unsigned int), G.stream));
     }
-    const size_t want = std::min<size_t>((size_t)G.wl_per_i * ni, (size_t)1 << 26);
+    const size_t want = std::min<size_t>((size_t)G.wl_per_i * ni, (size_t)1 << 28);   // <= 2 GiB of (i, slot) pairs
     if (want > G.wl_cap) {
         CK(cudaStreamSynchronize(G.stream));
         dev_free(G.d_wl);
@@ -1147,7 +1148,7 @@ static void open_context(int dev)   // g_cur selected by the caller
         e = getenv("G6_B200_FARC");
         G.farc = (e && *e) ? (float)atof(e) : 0.125f;
         G.near_w = std::max(1, env_int("G6_B200_NEAR_WINDOW", 32));
-        G.wl_per_i = std::max(1, env_int("G6_B200_WL_PER_I", 512));
+        G.wl_per_i = std::max(1, env_int("G6_B200_WL_PER_I", 1024));
     }
     host_alloc(G.h_i, (size_t)4 * G.npipes);
     dev_alloc(G.d_i, (size_t)4 * G.npipes);
@@ -2033,7 +2034,14 @@ static int calc_device_impl(int nj, int ni, const int *d_index, const double *d_
     Context::Peer &P = G.peer;
     ExchangeSlots ex{};
     if (exchange) ex = exchange_begin(ni, "g6x_calc_device_allreduce");
-    const int njc = std::min(nj, G.capacity);
+    // g6x_set_j_window: this process sums over a window of the slots only (every rank of a multi-process run holds
+    // all particles, like ph4's MPI ranks, and owns a contiguous piece of the Morton-ordered j-memory)
+    int wlo = 0, whi = std::min(nj, G.capacity);
+    if (G.cd_win_hi > 0) {
+        wlo = std::min(G.cd_win_lo, whi);
+        whi = std::min(G.cd_win_hi, whi);
+    }
+    const int njc = std::max(0, whi - wlo);
     const int chunk = device_chunk(ni, njc);
     if (chunk > G.i2_cap) {
         CK(cudaStreamSynchronize(G.stream));
@@ -2081,13 +2089,16 @@ static int calc_device_impl(int nj, int ni, const int *d_index, const double *d_
             const_cast<float4 *>(ib.C), const_cast<float4 *>(ib.D));
         G.launches++;
         CK(cudaGetLastError());
+        G.win_lo = wlo;
         if (!exchange) {
-            launch_force(nj, n, ib, (float)eps2, nn, false, d_sum + 7 * (size_t)ob, d_key + ob, d_nnid + ob);
+            launch_force(njc, n, ib, (float)eps2, nn, false, d_sum + 7 * (size_t)ob, d_key + ob, d_nnid + ob);
+            G.win_lo = 0;
             continue;
         }
         exchange_set_mirrors(ex, ob);
         unsigned char *own = ex.half[P.rank];
-        launch_force(nj, n, ib, (float)eps2, nn, false, slot_sum(own, ob), slot_key(own, ob), slot_id(own, ob));
+        launch_force(njc, n, ib, (float)eps2, nn, false, slot_sum(own, ob), slot_key(own, ob), slot_id(own, ob));
+        G.win_lo = 0;
         G.mir_n = 0;
     }
     if (exchange && ni > 0) exchange_finish(ni, d_sum, d_key, d_nnid);
@@ -2179,7 +2190,21 @@ int g6x_peer_error(void)
 int g6x_device_chunk(int ni)
 {
     require_open("g6x_device_chunk");
-    return device_chunk(ni, std::min(G.nj_hi, G.capacity));
+    int nj = std::min(G.nj_hi, G.capacity);
+    if (G.cd_win_hi > 0) nj = std::max(0, std::min(G.cd_win_hi, nj) - std::min(G.cd_win_lo, nj));
+    return device_chunk(ni, nj);
+}
+
+int g6x_set_j_window(int slot_lo, int slot_hi)
+{
+    require_open("g6x_set_j_window");
+    if (slot_hi > 0 && (slot_lo < 0 || slot_lo % TILE != 0 || slot_hi < slot_lo)) {
+        fprintf(stderr, "g6_b200: g6x_set_j_window: slot_lo must be a multiple of %d and <= slot_hi\n", TILE);
+        return -1;
+    }
+    G.cd_win_lo = slot_hi > 0 ? slot_lo : 0;
+    G.cd_win_hi = slot_hi > 0 ? slot_hi : 0;
+    return 0;
 }
 
 int g6x_resolve_nn(int ni, const unsigned long long *d_key, int rank, int *d_nnid)
@@ -2187,7 +2212,8 @@ int g6x_resolve_nn(int ni, const unsigned long long *d_key, int rank, int *d_nni
     require_open("g6x_resolve_nn");
     if (ni <= 0) return 0;
     resolve_nn_kernel<<<(ni + 255) / 256, 256, 0, G.stream>>>(ni, d_key, rank, G.j_offset,
-                                                               std::min(G.nj_hi, G.capacity), G.js.slot_of, G.js.B, d_nnid);
+                                                               std::min(G.nj_hi, G.capacity), G.js.slot_of, G.js.B, d_nnid,
+                                                               G.cd_win_lo, G.cd_win_hi > 0 ? G.cd_win_hi : 0x7fffffff);
     G.launches++;
     CK(cudaGetLastError());
     return 0;

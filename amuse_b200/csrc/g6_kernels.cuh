@@ -1895,7 +1895,8 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const ForceArgs p,
 // After a min-reduction of keys over ranks (each rank holds a j-shard): the id of the winner if this rank
 // owns it (keys carry the reported address = local address + j_offset).
 __global__ void resolve_nn_kernel(int ni, const u64 *__restrict__ key, int rank, int j_offset, int nj_local,
-                                  const int *__restrict__ slot_of, const float4 *__restrict__ jB, int *nnid)
+                                  const int *__restrict__ slot_of, const float4 *__restrict__ jB, int *nnid,
+                                  const int win_lo, const int win_hi)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= ni) return;
@@ -1905,7 +1906,10 @@ __global__ void resolve_nn_kernel(int ni, const u64 *__restrict__ key, int rank,
         id = (rank == 0) ? -1 : 0;
     } else {
         int a = (int)(unsigned)(k & 0xffffffffu) - j_offset;
-        if (a >= 0 && a < nj_local) id = __float_as_int(jB[slot_of[a]].w);
+        if (a >= 0 && a < nj_local) {   // this rank owns it if it holds the address and the slot is in its window
+            const int sl = slot_of[a];
+            if (sl >= win_lo && sl < win_hi) id = __float_as_int(jB[sl].w);
+        }
     }
     nnid[i] = id;
 }

@@ -31,7 +31,7 @@ G6_SYMBOLS = [
     "g6x_read_predicted", "g6x_time_predictor", "g6x_set_variant", "g6x_fp32_peak",
     "g6x_peer_handle_bytes", "g6x_peer_alloc", "g6x_peer_attach", "g6x_peer_detach", "g6x_peer_error",
     "g6x_calc_device_allreduce", "g6x_hermite_init", "g6x_hermite_step", "g6x_hermite_evolve", "g6x_hermite_get_state", "g6x_hermite_set_shard", "g6x_latency_probe",
-    "g6x_set_close_factor", "g6x_order_rebuilds", "g6x_device_count_open", "g6x_block_stats",
+    "g6x_set_close_factor", "g6x_order_rebuilds", "g6x_device_count_open", "g6x_block_stats", "g6x_set_j_window",
 ]
 
 _dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
@@ -67,6 +67,7 @@ def load():
     L.g6x_set_close_factor.argtypes = [C.c_double, C.c_double]
     L.g6x_order_rebuilds.restype = C.c_longlong
     L.g6x_block_stats.argtypes = [C.c_void_p]
+    L.g6x_set_j_window.argtypes = [C.c_int, C.c_int]
     L.g6x_set_j_offset.argtypes = [C.c_int]
     L.g6x_set_j_particles.argtypes = [C.c_int, C.c_void_p, C.c_int, _ip, C.c_void_p, _dp, C.c_void_p,
                                       C.c_void_p, _dp, _dp]

@@ -268,17 +268,23 @@ def run_b200(a):
     ids = np.arange(1, n + 1, dtype=np.int32)
     if a.shuffle_ids:      # ids unrelated to the addresses (a caller that does not load in id order)
         ids = (np.random.RandomState(11).permutation(n) + 1).astype(np.int32)
-    # j-domain of this rank: jdata::define_domain (src/amuse_ph4/src/jdata.cc:56-67)
-    j0, j1 = S.define_domain(n, world, rank)
+    # Like ph4's MPI ranks (jdata.cc:56-67 + idata.cc:147-237) every rank holds ALL particles and owns a contiguous
+    # j-domain -- here a window of the library's Morton-ordered j-memory (tile-aligned, define_window), so the close
+    # pairs the library evaluates in FP64 live on one or two ranks and the neighbour bounds are global
+    j0, j1 = 0, n
     os.environ.pop("G6_B200_DEVICES", None)
     g = g6lib.G6(local)
     L = g.L
     L.g6x_set_stream(C.c_void_p(torch.cuda.current_stream(dev).cuda_stream), 1)
-    L.g6x_set_j_offset(j0)
+    L.g6x_set_j_offset(0)
     if a.variant:
         g.set_variant(a.variant)
-    g.set_j_particles(ids[j0:j1], mass[j0:j1], pos[j0:j1], vel[j0:j1])
-    njl = j1 - j0
+    g.set_j_particles(ids, mass, pos, vel)
+    njl = n
+    w0, w1 = S.define_window(n, world, rank) if world > 1 else (0, 0)
+    if world > 1:
+        assert L.g6x_set_j_window(w0, w1) == 0
+    nj_own = (w1 - w0) if world > 1 else n
     if world > 1 and a.exchange == "peer":
         S.attach_peers(L, n)      # CUDA IPC handles gathered over the process group
     npipes = g.npipes
@@ -363,7 +369,7 @@ def run_b200(a):
     # (events bracket the force launches of one sweep: Morton sort of the i-set, packing, neighbour-bound pre-pass,
     # force kernel, FP64 pair kernel and partial reduction; the predictor is outside them)
     kms = np.array([e0.elapsed_time(e1) for e0, e1, _ in chunk_events]) / n_launch
-    flop_per_launch = FLOP_PER_INTERACTION * (float(n) / n_launch) * njl
+    flop_per_launch = FLOP_PER_INTERACTION * (float(n) / n_launch) * nj_own
     achieved = flop_per_launch / (kms.mean() * 1e-3) / 1e12
     kernel_share = float(kms.sum() * n_launch / ms_total)
 
@@ -488,6 +494,8 @@ def run_b200(a):
                                        n, a.eps2, dchunk, world),
                        "n": n, "eps2": a.eps2, "npipes": npipes, "i_per_launch": dchunk, "l2": "256 MiB buffer written between timed steps",
                        "ids": "shuffled against the addresses" if a.shuffle_ids else "1..N in address order",
+                       "j_domains": ("every rank holds all j and sums over its window of the Morton-ordered j-memory "
+                                     "(%d slots here)" % nj_own) if world > 1 else "all j on one device",
                        "parallelism": "j-shard x%d + %s" % (world, "none" if world == 1 else (
                            "peer-memory exchange fused into the force kernels (NVLink stores + combine kernel)"
                            if a.exchange == "peer" else "3 NCCL all-reduces"))},

@@ -207,6 +207,11 @@ int g6x_calc_device_allreduce(int nj, int ni, const int *d_index,
                               const double *d_h2, double eps2, int flags,
                               double *d_sum, unsigned long long *d_key,
                               int *d_nnid);
+/* Multi-process runs that replicate the j-memory (every rank loads ALL particles, like ph4's MPI ranks; the Morton
+ * order is then the same everywhere): this process' device-resident entry points sum over the slots
+ * [slot_lo, slot_hi) only (slot_lo a multiple of 256; the windows of all ranks tile [0, nj)).  The neighbour bounds
+ * that set the FP64 radius stay global, so no close pair is evaluated twice.  slot_hi <= 0: the whole j-memory. */
+int g6x_set_j_window(int slot_lo, int slot_hi);
 /* i-particles per kernel launch that g6x_calc_device uses for an i-set of ni against
  * the j currently loaded (it picks the chunk whose i-blocks x j-splits make four full
  * waves of CTAs with ~128 j-tiles each; g6_npipes_() only bounds the ABI path). */

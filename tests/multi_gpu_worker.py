@@ -1,5 +1,5 @@
-"""Worker of tests/test_gpu_multi.py, one rank per GPU (torchrun): j sharded over the ranks like
-jdata::define_domain (jdata.cc:56-67); the partial forces are combined (a) by the NCCL collectives of
+"""Worker of tests/test_gpu_multi.py, one rank per GPU (torchrun): every rank holds all particles and owns a
+j-domain like jdata::define_domain (jdata.cc:56-67); the partial forces are combined (a) by the NCCL collectives of
 amuse_b200/sharding.py and (b) inside the library over peer memory (g6x_calc_device_allreduce), and both
 are checked against the FP64 oracle on rank 0.  Prints one line 'MULTI-GPU OK ...' on success."""
 import ctypes as C
@@ -25,13 +25,15 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     m, x, v = P.new_plummer_model(n, seed=4)
     ids = np.arange(1, n + 1, dtype=np.int32)
-    j0, j1 = S.define_domain(n, world, rank)
+    # like ph4's MPI ranks every rank holds ALL particles and owns a contiguous j-domain: a window of the library's
+    # Morton-ordered j-memory (g6x_set_j_window), so neighbour bounds are global and no close pair is evaluated twice
     g = g6lib.G6(local)
     L = g.L
     L.g6x_set_stream(C.c_void_p(torch.cuda.current_stream(dev).cuda_stream), 1)
-    L.g6x_set_j_offset(j0)
-    g.set_j_particles(ids[j0:j1], m[j0:j1], x[j0:j1], v[j0:j1])
-    njl = j1 - j0
+    g.set_j_particles(ids, m, x, v)
+    njl = n
+    w0, w1 = S.define_window(n, world, rank)
+    assert L.g6x_set_j_window(w0, w1) == 0
     S.attach_peers(L, n)
 
     d_id = torch.from_numpy(ids).to(dev); d_x = torch.from_numpy(x).to(dev); d_v = torch.from_numpy(v).to(dev)

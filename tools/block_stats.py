@@ -24,6 +24,7 @@ ap.add_argument("--eps2", type=float, default=0.0)
 ap.add_argument("--abi-chunks", type=int, default=4)
 ap.add_argument("--sample", type=int, default=2048)
 ap.add_argument("--binaries", type=float, default=0.0)
+ap.add_argument("--jshard", type=int, default=1, help="load only the first 1/jshard of the particles as j (one rank of a sharded run)")
 a = ap.parse_args()
 
 dev = torch.device("cuda:0")
@@ -35,7 +36,8 @@ n = len(m)
 g = g6lib.G6(0)
 L = g.L
 L.g6x_set_stream(C.c_void_p(torch.cuda.current_stream(dev).cuda_stream), 1)
-g.set_j_particles(ids, m, x, v)
+nj = n // a.jshard
+g.set_j_particles(ids[:nj], m[:nj], x[:nj], v[:nj])
 d_id = torch.from_numpy(ids).to(dev)
 d_x = torch.from_numpy(x).to(dev)
 d_v = torch.from_numpy(v).to(dev)
@@ -47,7 +49,7 @@ have_stats = L.g6x_block_stats(st) == 0
 from oracle import oracle as O  # noqa: E402
 rnd = np.random.RandomState(5)
 samp = np.sort(rnd.choice(n, min(a.sample, n), replace=False))
-ref = O.force(x[samp], v[samp], m, x, v, a.eps2, iid=ids[samp], jid=ids)
+ref = O.force(x[samp], v[samp], m[:nj], x[:nj], v[:nj], a.eps2, iid=ids[samp], jid=ids[:nj])
 
 
 def errs(acc, jerk, pot):
@@ -73,13 +75,13 @@ for K in [float(t) for t in a.k.split(",")]:
         g.set_close_factor(K, farc)
         ts = []
         for r in range(3):
-            L.g6x_predict(n, 0.0)
+            L.g6x_predict(nj, 0.0)
             torch.cuda.synchronize()
             if r == 2:
                 stats()
             e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
             e0.record()
-            L.g6x_calc_device(n, n, d_id.data_ptr(), d_x.data_ptr(), d_v.data_ptr(), None, a.eps2, 1,
+            L.g6x_calc_device(nj, n, d_id.data_ptr(), d_x.data_ptr(), d_v.data_ptr(), None, a.eps2, 1,
                               d_sum.data_ptr(), d_key.data_ptr(), d_nn.data_ptr())
             e1.record()
             torch.cuda.synchronize()
@@ -87,7 +89,7 @@ for K in [float(t) for t in a.k.split(",")]:
         ms = min(ts[1:])
         s = d_sum[torch.from_numpy(samp).to(dev)].cpu().numpy()
         print("device path  K=%-4g farc=%-6g: %.1f ms/sweep %.4g int/s %.1f%% of nominal | %s%s" % (
-            K, farc, ms, float(n) * n / (ms * 1e-3), 100 * float(n) * n * 60 / (ms * 1e-3) / 74.45e12,
+            K, farc, ms, float(n) * nj / (ms * 1e-3), 100 * float(n) * nj * 60 / (ms * 1e-3) / 74.45e12,
             errs(s[:, 0:3], s[:, 3:6], -s[:, 6]), stats()), flush=True)
         if a.abi_chunks > 0:
             L.g6x_set_stream(None, 0)
