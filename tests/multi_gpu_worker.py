@@ -95,6 +95,7 @@ def main():
             r[0][0, 0].item()      # the caller reads the result every step
         dt = (time.perf_counter() - t0) / 50
         msgs.append("block step ni=37 %s: %.1f us" % ("peer-memory exchange" if fused else "3 NCCL all-reduces", dt * 1e6))
+    torch.cuda.synchronize(); dist.barrier()     # peers may still read this rank's exchange buffer: detach together
     g.close()
 
     # ---- sharded device-resident Hermite integrator: replicated state, sharded forces ----------------
@@ -123,6 +124,7 @@ def main():
     # all ranks must hold the same replica, bit for bit
     xs = torch.from_numpy(sharded[1]).to(dev); chk = xs.clone(); dist.all_reduce(chk, op=dist.ReduceOp.MAX)
     same_replica = bool((chk == xs).all().item())
+    torch.cuda.synchronize(); dist.barrier()
     g.close()
     dist.barrier()
     if rank == 0:                                           # the same run on one device

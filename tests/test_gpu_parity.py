@@ -352,9 +352,14 @@ def test_neighbour_lists(g6):
         if not good:
             bad.append((i, rc, n, n_ref, int(out["nn"][i]), int(ids[f["nn"][i]]), lst[:6].tolist(), lst_ref[:6].tolist()))
     assert not bad, bad[:10]
-    # overflow flag: tiny maxlength
-    rc, n, lst = g6.get_neighbour_list(0, maxlength=1)
-    assert n >= 1 and (rc != 0) == (n > 1)
+    # overflow flag: nblen >= maxlength (lib/sapporo_light/sapporo.cpp:262-265; ph4 shrinks h2 on it, gpu.cc:668-751)
+    k = int(np.argmax([g6.get_neighbour_list(i)[1] for i in range(300)]))
+    rc, n, lst = g6.get_neighbour_list(k)
+    assert n >= 2
+    for maxlength, want in ((n + 1, 0), (n, 1), (n - 1, 1), (1, 1)):
+        rc, n2, lst2 = g6.get_neighbour_list(k, maxlength=maxlength)
+        assert n2 == n and (rc != 0) == bool(want), (maxlength, rc, n2)
+        assert np.array_equal(lst2, lst[:min(n, maxlength)])
     # h2 = 0 everywhere -> no lists
     g6.calc(ids[:10], x[:10], v[:10], 0.0)
     assert g6.read_neighbour_list() == 0

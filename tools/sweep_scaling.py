@@ -21,7 +21,7 @@ for n in [int(s) for s in a.sizes.split(",")]:
         cmd += ["-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(a.gpus), "--master-addr", "127.0.0.1",
                 "--master-port", "29533"]
     cmd += [os.path.join(ROOT, "bench.py"), "--gpus", str(a.gpus), "--steps", str(steps), "--warmup", str(warm),
-            "--particles", str(n), "--no-e2e", "--no-cpu-baseline"]
+            "--particles", str(n), "--no-e2e", "--no-cpu-baseline", "--no-extras", "--parity-sample", "0"]
     out = subprocess.run(cmd, capture_output=True, text=True)
     lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
     if not lines:
