@@ -683,7 +683,7 @@ void launch_inline(const ForceArgs &a, dim3 grid, const InlineI<INL> &ii, cudaSt
 template <int IPT, int MINB>
 void launch_fast(const ForceArgs &a, dim3 grid, bool nn, cudaStream_t st)
 {
-    size_t smem = sizeof(ForceSmem);
+    size_t smem = sizeof(FastSmem);
     const bool eps0 = (a.eps2 == 0.f);   // unsoftened: the 2^-52 of the reference is handled by the verification
 #define G6_LAUNCH(NN_, NR_)                                                                         \
     do {                                                                                            \

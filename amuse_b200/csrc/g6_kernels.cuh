@@ -914,6 +914,21 @@ struct __align__(16) ForceSmem {
     int2 wl[CTA_WL];          // (packed i, slot)
 };
 
+// force_fast_kernel: a deeper pipeline and no CTA-wide barrier per tile.  The warps of a CTA take different
+// times over a tile (a warp whose particles have FP64 pairs in it runs the masked loop, the others the
+// mask-free one), so each warp releases a stage on its own (done[s]) and the last one to do so refills it;
+// a warp may run up to FSTAGES - 1 tiles ahead of the slowest.
+constexpr int FSTAGES = 8;
+struct __align__(16) FastSmem {
+    float4 A[FSTAGES][TILE];
+    float4 B[FSTAGES][TILE];
+    float4 C[FSTAGES][TILE];
+    float4 G[FSTAGES][TBOX];
+    uint64_t full[FSTAGES];
+    unsigned int done[FSTAGES];   // warps that have finished with the stage's current tile
+    unsigned int is_last;
+};
+
 __device__ __forceinline__ u64 make_key(float r2min, int jmin)
 {
     return ((u64)(unsigned)__float_as_int(r2min) << 32) | (u64)(unsigned)jmin;
@@ -1480,7 +1495,7 @@ __global__ void __launch_bounds__(THREADS, MINB) force_fast_kernel(const __grid_
     const float INF = __int_as_float(0x7f800000);
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    ForceSmem &sm = *reinterpret_cast<ForceSmem *>(smem_raw);
+    FastSmem &sm = *reinterpret_cast<FastSmem *>(smem_raw);
     const int tid = threadIdx.x;
 
     const int ntiles_total = (p.nj + TILE - 1) / TILE;
@@ -1491,7 +1506,10 @@ __global__ void __launch_bounds__(THREADS, MINB) force_fast_kernel(const __grid_
     auto tile_of = [&](const int t) -> int { return (int)blockIdx.x + t * tstride; };
 
     if (tid == 0) {
-        for (int s = 0; s < STAGES; s++) mbar_init(&sm.full[s], 1);
+        for (int s = 0; s < FSTAGES; s++) {
+            mbar_init(&sm.full[s], 1);
+            sm.done[s] = 0u;
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -1505,7 +1523,7 @@ __global__ void __launch_bounds__(THREADS, MINB) force_fast_kernel(const __grid_
         bulk_g2s(sm.G[s], p.jG + (size_t)tile * TBOX, TBOX * sizeof(float4), &sm.full[s]);
     };
     if (tid == 0)
-        for (int s = 0; s < STAGES && s < ntiles; s++) issue_stage(s, tile_of(s));
+        for (int s = 0; s < FSTAGES && s < ntiles; s++) issue_stage(s, tile_of(s));
 
     // ---- register-resident i-pairs: i = block base + IPT*tid + k (consecutive = Morton neighbours) --------
     IPair IP[NP];
@@ -1591,8 +1609,8 @@ __global__ void __launch_bounds__(THREADS, MINB) force_fast_kernel(const __grid_
 #endif
 
     for (int t = 0; t < ntiles; t++) {
-        const int s = t % STAGES;
-        const uint32_t phase = (uint32_t)(t / STAGES) & 1u;
+        const int s = t % FSTAGES;
+        const uint32_t phase = (uint32_t)(t / FSTAGES) & 1u;
         while (!mbar_try_wait(&sm.full[s], phase)) {
         }
         const int jtile = tile_of(t) * TILE;
@@ -1787,8 +1805,17 @@ __global__ void __launch_bounds__(THREADS, MINB) force_fast_kernel(const __grid_
             }
         }
 
-        __syncthreads();  // everyone is done with stage s
-        if (tid == 0 && t + STAGES < ntiles) issue_stage(s, tile_of(t + STAGES));
+        // this warp is done with stage s; the last warp of the CTA to say so refills it
+        __syncwarp();
+        if ((tid & 31) == 0) {
+            unsigned int old;
+            asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;"
+                         : "=r"(old) : "r"((uint32_t)__cvta_generic_to_shared(&sm.done[s])) : "memory");
+            if (old == (unsigned)(THREADS / 32 - 1)) {
+                sm.done[s] = 0u;
+                if (t + FSTAGES < ntiles) issue_stage(s, tile_of(t + FSTAGES));
+            }
+        }
     }
 
 #ifdef G6_STATS
