@@ -111,6 +111,7 @@ struct Context {
     float kclose = 32.f;               // G6_B200_KCLOSE
     float farc = 0.125f;               // G6_B200_FARC
     int near_w = 32;                   // Morton window (each side) of the neighbour-bound scans
+    int gmax = 256;                    // G6_B200_GMAX: group boxes a particle's FP64 radius may touch
     unsigned long long *d_stats = nullptr;   // block-class counters (-DG6_STATS builds)
     // FP64 pairs: global list of the speculative kernel + per-particle results (see ForceArgs)
     int2 *d_wl = nullptr;
@@ -322,6 +323,8 @@ void ensure_capacity(int need)
     for (int k = 0; k < 7; k++) { dev_free(G.js2.q[k]); dev_alloc(G.js2.q[k], newcap); }
     dev_free(G.js2.ia); dev_alloc(G.js2.ia, newcap);
     dev_free(G.js2.near2); dev_alloc(G.js2.near2, newcap);
+    dev_free(G.js.capr2); dev_alloc(G.js.capr2, newcap);   // filled by the re-ordering that follows every growth
+    G.js2.capr2 = G.js.capr2;
     dev_free(G.addr_of2); dev_alloc(G.addr_of2, newcap);
     dev_free(G.d_keys); dev_alloc(G.d_keys, newcap);
     dev_free(G.d_keys_tmp); dev_alloc(G.d_keys_tmp, newcap);
@@ -570,9 +573,18 @@ void rebuild_order(int nj)
     G.ord.nkeys = nprefix;
     order_near_kernel<<<(nprefix + 255) / 256, 256, 0, st>>>(nprefix, G.js, G.near_w);
     CK(cudaGetLastError());
+    // cap of the FP64 radius (particles whose K d^2 would reach a large part of the system)
+    {
+        const int ntiles = (nprefix + TILE - 1) / TILE;
+        order_boxes_kernel<<<ntiles, TILE, 0, st>>>(nprefix, G.js);
+        CK(cudaGetLastError());
+        order_cap_kernel<<<(nprefix + 255) / 256, 256, 0, st>>>(nprefix, G.js, ntiles,
+                                                                G.order_tiny ? 0x7fffffff : G.gmax);
+        CK(cudaGetLastError());
+    }
     CK(cudaMemcpyAsync(G.h_slot_of.data(), G.js.slot_of, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    G.launches += 8;
+    G.launches += 10;
     G.j_dirty = true;       // slots moved and the origin changed: predict again
     G.predicted_nj = -1;
 }
@@ -634,10 +646,10 @@ void launch_variant_nr(const ForceArgs &a, dim3 grid, bool nn, bool list, cudaSt
 #define G6_LAUNCH(NN_, LIST_)                                                                       \
     do {                                                                                            \
         auto kern = force_kernel<IPT, NI_SLOTS, NN_, LIST_, PACKED, NR, MINB, 0>;                   \
-        static bool attr_set = false;                                                               \
-        if (!attr_set) {                                                                            \
+        static bool attr_set[64] = {}; /* per device */                                                               \
+        if (!attr_set[G.device & 63]) {                                                                            \
             CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            attr_set = true;                                                                        \
+            attr_set[G.device & 63] = true;                                                                        \
         }                                                                                           \
         kern<<<grid, THREADS, smem, st>>>(a, none);                                                 \
     } while (0)
@@ -668,10 +680,10 @@ void launch_inline(const ForceArgs &a, dim3 grid, const InlineI<INL> &ii, cudaSt
 #define G6_LAUNCH(NR_)                                                                              \
     do {                                                                                            \
         auto kern = force_kernel<IPT, NI_SLOTS, true, false, PACKED, NR_, MINB, INL>;               \
-        static bool attr_set = false;                                                               \
-        if (!attr_set) {                                                                            \
+        static bool attr_set[64] = {}; /* per device */                                                               \
+        if (!attr_set[G.device & 63]) {                                                                            \
             CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            attr_set = true;                                                                        \
+            attr_set[G.device & 63] = true;                                                                        \
         }                                                                                           \
         kern<<<grid, THREADS, smem, st>>>(a, ii);                                                   \
     } while (0)
@@ -692,10 +704,10 @@ void launch_fast(const ForceArgs &a, dim3 grid, bool nn, cudaStream_t st)
 #define G6_LAUNCH2(NN_, NR_, E0_)                                                                   \
     do {                                                                                            \
         auto kern = force_fast_kernel<IPT, NN_, NR_, MINB, E0_>;                                    \
-        static bool attr_set = false;                                                               \
-        if (!attr_set) {                                                                            \
+        static bool attr_set[64] = {}; /* per device */                                                               \
+        if (!attr_set[G.device & 63]) {                                                                            \
             CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            attr_set = true;                                                                        \
+            attr_set[G.device & 63] = true;                                                                        \
         }                                                                                           \
         kern<<<grid, THREADS, smem, st>>>(a);                                                       \
     } while (0)
@@ -718,10 +730,10 @@ void launch_herm(const ForceArgs &a, dim3 grid, cudaStream_t st)
 #define G6_LAUNCH(NR_)                                                                              \
     do {                                                                                            \
         auto kern = force_kernel<IPT, NI_SLOTS, true, false, PACKED, NR_, MINB, 0, true>;           \
-        static bool attr_set = false;                                                               \
-        if (!attr_set) {                                                                            \
+        static bool attr_set[64] = {}; /* per device */                                                               \
+        if (!attr_set[G.device & 63]) {                                                                            \
             CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            attr_set = true;                                                                        \
+            attr_set[G.device & 63] = true;                                                                        \
         }                                                                                           \
         kern<<<grid, THREADS, smem, st>>>(a, none);                                                 \
     } while (0)
@@ -964,7 +976,7 @@ bool is_fast_variant(int v) { return v == V_F2 || v == V_F4; }
 void free_all()
 {
     for (int k = 0; k < 7; k++) { dev_free(G.js.q[k]); dev_free(G.js2.q[k]); }
-    dev_free(G.js.ia); dev_free(G.js2.ia); dev_free(G.js.near2); dev_free(G.js2.near2);
+    dev_free(G.js.ia); dev_free(G.js2.ia); dev_free(G.js.near2); dev_free(G.js2.near2); dev_free(G.js.capr2); G.js2.capr2 = nullptr;
     dev_free(G.js.A); dev_free(G.js.B); dev_free(G.js.C); dev_free(G.js.L); dev_free(G.js.gbb);
     dev_free(G.js.slot_of); dev_free(G.addr_of); dev_free(G.addr_of2);
     dev_free(G.d_keys); dev_free(G.d_keys_tmp); dev_free(G.d_vals); dev_free(G.d_vals_tmp);
@@ -1148,6 +1160,7 @@ static void open_context(int dev)   // g_cur selected by the caller
         e = getenv("G6_B200_FARC");
         G.farc = (e && *e) ? (float)atof(e) : 0.125f;
         G.near_w = std::max(1, env_int("G6_B200_NEAR_WINDOW", 32));
+        G.gmax = std::max(1, env_int("G6_B200_GMAX", 256));
         G.wl_per_i = std::max(1, env_int("G6_B200_WL_PER_I", 1024));
     }
     host_alloc(G.h_i, (size_t)4 * G.npipes);

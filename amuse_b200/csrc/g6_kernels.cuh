@@ -72,6 +72,8 @@ struct JState {
     int *slot_of;        // [address] -> slot
     float *near2;        // [slot] squared distance to the nearest neighbour when the particle was last an
                          // i-particle (or an upper bound from the Morton window at the last re-ordering)
+    float *capr2;        // [slot] largest FP64 radius^2 the particle may use: the radius within which it touches no
+                         // more than gmax group boxes (order_cap_kernel; one buffer shared by both array sets)
     double x0[3];        // origin subtracted from every position before the hi/lo split
 };
 
@@ -795,7 +797,7 @@ __device__ __forceinline__ float close_radius2(const ForceArgs &p, const int iid
     const float4 a = p.js.A[s], b = p.js.B[s];
     const float dx = (a.x - xh) + (b.x - xl), dy = (a.y - yh) + (b.y - yl), dz = (a.z - zh) + (b.z - zl);
     const float d = sqrtf(dx * dx + dy * dy + dz * dz) + sqrtf(p.js.near2[s]);
-    return fminf(p.ord.kclose * d * d, p.ord.cap2);
+    return fminf(fminf(p.ord.kclose * d * d, p.ord.cap2), p.js.capr2[s]);
 }
 
 // Split reduction shared by the force kernels: the last CTA of an i-block (ticket) sums the
@@ -1460,10 +1462,11 @@ __global__ void __launch_bounds__(256) near_kernel(const ForceArgs p, const int 
     const float4 a = p.iA[i], b = p.iB[i];
     const int iid = __float_as_int(b.w);
     const int self = hash_lookup(p.ord, iid);
-    float d2 = __int_as_float(0x7f800000);
+    float d2 = __int_as_float(0x7f800000), cap = __int_as_float(0x7f800000);
     if (p.ord.nkeys > 0) {
         int s = self;
         if (s < 0 || s >= p.ord.nkeys) s = key_search(p.ord, morton30(a.x, a.y, a.z, p.ord.blo, p.ord.binv));
+        cap = p.js.capr2[s];
         const int lo = max(0, s - W), hi = min(p.ord.nkeys, s + W + 1);
         for (int j = lo + lane; j < hi; j += 32) {
             const float4 ja = p.js.A[j], jb = p.js.B[j];
@@ -1479,6 +1482,9 @@ __global__ void __launch_bounds__(256) near_kernel(const ForceArgs p, const int 
         float4 d = p.iD[i];
         d.w = d2 * 1.0001f;   // the kernel's own r2 of that pair may round differently
         const_cast<float4 *>(p.iD)[i] = d;
+        float4 c = p.iC[i];
+        c.w = cap;            // cap of the FP64 radius^2 (order_cap_kernel) of the slot the particle sits on
+        const_cast<float4 *>(p.iC)[i] = c;
     }
 }
 
@@ -1553,7 +1559,7 @@ __global__ void __launch_bounds__(THREADS, MINB) force_fast_kernel(const __grid_
                 const float d2 = p.iD[i].w;
                 const int cf = p.conf[i];
                 d2k[k] = d2;
-                closek[k] = (p.ord.kclose > 0.f) ? fminf(p.ord.kclose * d2, p.ord.cap2) : -1.f;
+                closek[k] = (p.ord.kclose > 0.f) ? fminf(fminf(p.ord.kclose * d2, p.ord.cap2), c[h].w) : -1.f;
                 closemax = fmaxf(closemax, closek[k]);
                 nnmax = fmaxf(nnmax, d2);
                 several |= (cf == -2);
@@ -2041,6 +2047,122 @@ __global__ void __launch_bounds__(256) order_near_kernel(const int n, const JSta
         }
     }
     s.near2[j] = d2;
+}
+// Group and tile boxes of the STATE positions (same layout as predict_tile's, which overwrites them at the next
+// prediction): what order_cap_kernel measures against.  One CTA per tile, one warp per group.
+__global__ void __launch_bounds__(TILE) order_boxes_kernel(const int n, const JState s)
+{
+    __shared__ int sh[6][TILE / 32];
+    const int j = blockIdx.x * TILE + threadIdx.x;   // < capacity (whole tiles)
+    const bool massive = (j < n) && (s.q[6][j].y > (double)TINYF);
+    float x = 0.f, y = 0.f, z = 0.f;
+    if (massive) {
+        x = (float)(s.q[0][j].x - s.x0[0]);
+        y = (float)(s.q[0][j].y - s.x0[1]);
+        z = (float)(s.q[1][j].x - s.x0[2]);
+    }
+    const int big = 0x7f7fffff, small = f2ord(-3.0e38f);
+    const int lx = __reduce_min_sync(0xffffffffu, massive ? f2ord(x) : big);
+    const int ly = __reduce_min_sync(0xffffffffu, massive ? f2ord(y) : big);
+    const int lz = __reduce_min_sync(0xffffffffu, massive ? f2ord(z) : big);
+    const int hx = __reduce_max_sync(0xffffffffu, massive ? f2ord(x) : small);
+    const int hy = __reduce_max_sync(0xffffffffu, massive ? f2ord(y) : small);
+    const int hz = __reduce_max_sync(0xffffffffu, massive ? f2ord(z) : small);
+    const int w = threadIdx.x >> 5;
+    float4 *tb = s.gbb + (size_t)blockIdx.x * TBOX;
+    if ((threadIdx.x & 31) == 0) {
+        tb[2 * w] = make_float4(ord2f(lx), ord2f(ly), ord2f(lz), 0.f);
+        tb[2 * w + 1] = make_float4(ord2f(hx), ord2f(hy), ord2f(hz), 0.f);
+        sh[0][w] = lx; sh[1][w] = ly; sh[2][w] = lz; sh[3][w] = hx; sh[4][w] = hy; sh[5][w] = hz;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int r[6];
+#pragma unroll
+        for (int q = 0; q < 6; q++) r[q] = sh[q][0];
+#pragma unroll
+        for (int g = 1; g < TILE / 32; g++) {
+#pragma unroll
+            for (int q = 0; q < 3; q++) r[q] = min(r[q], sh[q][g]);
+#pragma unroll
+            for (int q = 3; q < 6; q++) r[q] = max(r[q], sh[q][g]);
+        }
+        tb[2 * GROUPS_PER_TILE] = make_float4(ord2f(r[0]), ord2f(r[1]), ord2f(r[2]), 0.f);
+        tb[2 * GROUPS_PER_TILE + 1] = make_float4(ord2f(r[3]), ord2f(r[4]), ord2f(r[5]), 0.f);
+    }
+}
+// Cap of every particle's FP64 radius.  The radius K d^2 is meant to hold the few hundred strongest pairs of a
+// particle; for a particle of the halo whose nearest neighbour is far away while the dense core is not, it would
+// hold a large part of the system (a few particles in a thousand, which then dominate the FP64 work and make
+// their whole warp take the masked path against every group).  Such pairs are many and comparable, their FP32
+// errors average out like those of the far field, so the radius is cut back to the largest of
+// 64 d^2 / 2^b (b = 0..5) within which the particle touches at most gmax group boxes (never below 2 d^2: the
+// nearest neighbour stays inside).  d^2 = near2 (the bound from the Morton window).
+constexpr int CAP_BINS = 6;
+__global__ void __launch_bounds__(256) order_cap_kernel(const int n, const JState s, const int ntiles, const int gmax)
+{
+    __shared__ float4 tb[2 * 256];
+    const int j = blockIdx.x * 256 + threadIdx.x;
+    const float INF = __int_as_float(0x7f800000);
+    float near2 = (j < n) ? s.near2[j] : INF;
+    const bool live = (j < n) && (s.q[6][j].y > (double)TINYF) && (near2 < 1.0e30f) && (near2 > 0.f);
+    float x = 0.f, y = 0.f, z = 0.f;
+    if (live) {
+        x = (float)(s.q[0][j].x - s.x0[0]);
+        y = (float)(s.q[0][j].y - s.x0[1]);
+        z = (float)(s.q[1][j].x - s.x0[2]);
+    }
+    const float c0 = 64.f * near2;
+    int cnt[CAP_BINS];
+#pragma unroll
+    for (int b = 0; b < CAP_BINS; b++) cnt[b] = 0;
+    auto gap2 = [&](const float4 lo, const float4 hi) -> float {
+        const float gx = fmaxf(0.f, fmaxf(lo.x - x, x - hi.x)), gy = fmaxf(0.f, fmaxf(lo.y - y, y - hi.y)),
+                    gz = fmaxf(0.f, fmaxf(lo.z - z, z - hi.z));
+        return gx * gx + gy * gy + gz * gz;
+    };
+    for (int t0 = 0; t0 < ntiles; t0 += 256) {
+        __syncthreads();
+        if (t0 + (int)threadIdx.x < ntiles) {
+            const float4 *g = s.gbb + (size_t)(t0 + threadIdx.x) * TBOX;
+            tb[2 * threadIdx.x] = g[2 * GROUPS_PER_TILE];
+            tb[2 * threadIdx.x + 1] = g[2 * GROUPS_PER_TILE + 1];
+        }
+        __syncthreads();
+        const int m = min(256, ntiles - t0);
+        if (live) {
+            for (int u = 0; u < m; u++) {
+                if (gap2(tb[2 * u], tb[2 * u + 1]) <= c0) {
+                    const float4 *g = s.gbb + (size_t)(t0 + u) * TBOX;
+                    for (int k = 0; k < GROUPS_PER_TILE; k++) {
+                        const float d2 = gap2(g[2 * k], g[2 * k + 1]);
+                        float c = c0;
+#pragma unroll
+                        for (int b = 0; b < CAP_BINS; b++) {
+                            cnt[b] += (d2 <= c) ? 1 : 0;
+                            c *= 0.5f;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (j < n) {
+        float cap = INF;
+        if (live && cnt[0] > gmax) {
+            cap = c0 * (1.f / (float)(1 << (CAP_BINS - 1)));
+            float c = c0;
+#pragma unroll
+            for (int b = 1; b < CAP_BINS; b++) {
+                c *= 0.5f;
+                if (cnt[b] <= gmax) {
+                    cap = c;
+                    break;
+                }
+            }
+        }
+        s.capr2[j] = cap;
+    }
 }
 // Morton keys of an i-set (device-resident callers), for the sort that precedes pack_i_kernel
 __global__ void __launch_bounds__(256) i_key_kernel(const int ni, const double *__restrict__ xi, const JState s,

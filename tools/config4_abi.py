@@ -93,7 +93,7 @@ def main():
                 "r = O.ref_evolve_enc(m, x, v, 0.0, 0.14, 1.0, manage_encounters=%%d, ids=ids, use_gpu=True, "
                 "max_block_steps=%d); print('RESULT ' + json.dumps({k: float(v_) for k, v_ in r.items()}))") % (ROOT, n0, ph4_steps)
         res["ph4"] = {}
-        for mode in (1, 0):
+        for mode in ((1,) if os.environ.get("CONFIG4_ENC_ONLY") else (1, 0)):
             t0 = time.perf_counter()
             p = subprocess.run([sys.executable, "-c", code % mode], capture_output=True, text=True, timeout=3000)
             line = [l for l in p.stdout.splitlines() if l.startswith("RESULT ")]
