@@ -231,7 +231,10 @@ __device__ __forceinline__ void apply_updates(const InlineU &iu, const JUpdate *
     __syncthreads();   // the block's own global writes are visible to its threads after the barrier
 }
 
-__global__ void __launch_bounds__(TILE) predict_kernel(int n, double ti, JState s, int tile0 = 0)
+#ifndef G6_PRED_MINB
+#define G6_PRED_MINB 5   // CTAs per SM the predictor is compiled for (48 registers): loads in flight, not arithmetic, bound it
+#endif
+__global__ void __launch_bounds__(TILE, G6_PRED_MINB) predict_kernel(int n, double ti, JState s, int tile0 = 0)
 {
     predict_tile(tile0 + blockIdx.x, n, ti, s);
 }
@@ -1022,24 +1025,30 @@ __global__ void __launch_bounds__(THREADS, MINB) force_kernel(const __grid_const
         }
     }
     const double eps2t = (double)p.eps2 + (double)TINYF;
-    // pair (k, slot j of this launch's window) to be evaluated in FP64: queued for the dense pass after the tile
-    // loop; without a corr buffer (or with the queue full) evaluated here and added to D[k]
-    auto close_pair = [&](const int k, const float4 a, const float4 b, const float4 c, const int jlocal, double *Dk) {
+    // Pairs (k, slot j of this launch's window) to be evaluated in FP64 are collected as bits per particle over a
+    // flush group (no branch in the pair loop: with ~1.5 % of the pairs inside an FP64 radius nearly every
+    // warp-iteration would diverge), then queued with one shared-memory atomic per particle and group for the
+    // dense pass after the tile loop; without a corr buffer (or with the queue full) evaluated here into D[k].
+    // bit u of bits: the pair with j = jbase + u * NJ_SLOTS.
+    auto flush_close = [&](const int k, unsigned int bits, const int jbase, double *Dk) {
         const int i = i_of(k);
-        if (p.corr) {
-            const unsigned int e = atomicAdd(&sm.wl_n, 1u);
+        unsigned int e = p.corr ? atomicAdd(&sm.wl_n, (unsigned)__popc(bits)) : (unsigned)CTA_WL;
+        while (bits) {
+            const int u = __ffs(bits) - 1;
+            bits &= bits - 1u;
+            const int jlocal = jbase + u * NJ_SLOTS;
             if (e < (unsigned)CTA_WL) {
-                sm.wl[e] = make_int2(i, jlocal);
-                return;
+                sm.wl[e++] = make_int2(i, jlocal);
+                continue;
             }
-        }
-        const float4 d = (INL > 0) ? ii.d[3 * INL + i] : p.iD[i];
-        F64Out o;
-        fp64_pair(&o, a, b, c, p.jL[jlocal], (double)xh[k] + (double)xl[k], (double)yh[k] + (double)yl[k],
-                  (double)zh[k] + (double)zl[k], (double)vx[k] + (double)d.x, (double)vy[k] + (double)d.y,
-                  (double)vz[k] + (double)d.z, eps2t);
+            const float4 d = (INL > 0) ? ii.d[3 * INL + i] : p.iD[i];
+            F64Out o;
+            fp64_pair(&o, p.jA[jlocal], p.jB[jlocal], p.jC[jlocal], p.jL[jlocal], (double)xh[k] + (double)xl[k],
+                      (double)yh[k] + (double)yl[k], (double)zh[k] + (double)zl[k], (double)vx[k] + (double)d.x,
+                      (double)vy[k] + (double)d.y, (double)vz[k] + (double)d.z, eps2t);
 #pragma unroll
-        for (int q = 0; q < 7; q++) Dk[q] += o.v[q];
+            for (int q = 0; q < 7; q++) Dk[q] += o.v[q];
+        }
     };
 
     double D[IPT][7];
@@ -1101,7 +1110,10 @@ __global__ void __launch_bounds__(THREADS, MINB) force_kernel(const __grid_const
                 Acc7 S[IPT];
 #pragma unroll
                 for (int k = 0; k < IPT; k++) S[k] = Acc7{0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                auto do_j = [&](int jj) {
+                unsigned int hb[IPT];
+#pragma unroll
+                for (int k = 0; k < IPT; k++) hb[k] = 0u;
+                auto do_j = [&](const int jj, const int u) {
                     const float4 a = tA[jj], b = tB[jj], c = tC[jj];
                     const int jaddr = jtile + jj;
 #pragma unroll
@@ -1109,15 +1121,19 @@ __global__ void __launch_bounds__(THREADS, MINB) force_kernel(const __grid_const
                         const bool hp = interact<NN, LIST, NR>(a, b, c, jaddr, xh[k], yh[k], zh[k], xl[k], yl[k], zl[k],
                                                                vx[k], vy[k], vz[k], iid[k], h2[k], eps2, thr[k], S[k],
                                                                r2min[k], jmin[k], i_of(k), p);
-                        if (hp) close_pair(k, a, b, c, jaddr, D[k]);
+                        hb[k] |= (hp ? 1u : 0u) << u;
                     }
                 };
                 if (whole) {
 #pragma unroll UNROLL
-                    for (int u = 0; u < FL; u++) do_j(jj0 + u * NJ_SLOTS);
+                    for (int u = 0; u < FL; u++) do_j(jj0 + u * NJ_SLOTS, u);
                 } else {
-                    for (int jj = jj0; jj < cnt; jj += NJ_SLOTS) do_j(jj);
+                    int u = 0;
+                    for (int jj = jj0; jj < cnt; jj += NJ_SLOTS) do_j(jj, u++);
                 }
+#pragma unroll
+                for (int k = 0; k < IPT; k++)
+                    if (hb[k]) flush_close(k, hb[k], jtile + jj0, D[k]);
 #pragma unroll
                 for (int k = 0; k < IPT; k++) {
                     D[k][0] += (double)S[k].ax; D[k][1] += (double)S[k].ay; D[k][2] += (double)S[k].az;
@@ -1128,7 +1144,10 @@ __global__ void __launch_bounds__(THREADS, MINB) force_kernel(const __grid_const
                 Acc7P S[NP];
 #pragma unroll
                 for (int q = 0; q < NP; q++) S[q] = Acc7P{0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull};
-                auto do_j = [&](int jj) {
+                unsigned int hb[IPT];
+#pragma unroll
+                for (int k = 0; k < IPT; k++) hb[k] = 0u;
+                auto do_j = [&](const int jj, const int u) {
                     const float4 a = tA[jj], b = tB[jj], c = tC[jj];
                     const int jaddr = jtile + jj;
 #pragma unroll
@@ -1136,18 +1155,20 @@ __global__ void __launch_bounds__(THREADS, MINB) force_kernel(const __grid_const
                         const int hpm = interact2<NN, LIST, NR>(a, b, c, jaddr, IP[q], eps2p, thr[2 * q], thr[2 * q + 1],
                                                                 S[q], r2min[2 * q], jmin[2 * q], r2min[2 * q + 1],
                                                                 jmin[2 * q + 1], i_of(2 * q), p);
-                        if (hpm) {
-                            if (hpm & 1) close_pair(2 * q, a, b, c, jaddr, D[2 * q]);
-                            if (hpm & 2) close_pair(2 * q + 1, a, b, c, jaddr, D[2 * q + 1]);
-                        }
+                        hb[2 * q] |= (unsigned)(hpm & 1) << u;
+                        hb[2 * q + 1] |= (unsigned)((hpm >> 1) & 1) << u;
                     }
                 };
                 if (whole) {
 #pragma unroll UNROLL
-                    for (int u = 0; u < FL; u++) do_j(jj0 + u * NJ_SLOTS);
+                    for (int u = 0; u < FL; u++) do_j(jj0 + u * NJ_SLOTS, u);
                 } else {
-                    for (int jj = jj0; jj < cnt; jj += NJ_SLOTS) do_j(jj);
+                    int u = 0;
+                    for (int jj = jj0; jj < cnt; jj += NJ_SLOTS) do_j(jj, u++);
                 }
+#pragma unroll
+                for (int k = 0; k < IPT; k++)
+                    if (hb[k]) flush_close(k, hb[k], jtile + jj0, D[k]);
 #pragma unroll
                 for (int q = 0; q < NP; q++) {
                     float lo, hi;

@@ -12,9 +12,10 @@ if '--seq' in sys.argv:
     for r in rows[1:]:
         print("%10.2f us  %s" % (float(r[vi].replace(',', '')) * scale.get(r[ui], 1e-3), r[ki][:90]))
     sys.exit(0)
+gi = h.index('Grid Size') if 'Grid Size' in h else None
 d = collections.defaultdict(lambda: [0, 0.0])
 for r in rows[1:]:
-    k = r[ki][:80]
+    k = r[ki][:60] + ((" grid " + r[gi]) if gi is not None and '--grid' in sys.argv else "")
     d[k][0] += 1
     d[k][1] += float(r[vi].replace(',', '')) * scale.get(r[ui], 1e-3)
 tot = sum(v[1] for v in d.values())
