@@ -189,6 +189,25 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def _committed_traffic():
+    """DRAM bytes of one force-kernel launch from the committed `ncu --set full` capture of this bench command
+    (profiles/r02_force_kernel_ncu.txt: dram__bytes_read.sum + dram__bytes_write.sum, 16384 i x 1M j launch); DRAM
+    counters cannot be read without the profiler, so the run itself reports the committed figure or null."""
+    path = os.path.join(ROOT, "profiles", "r02_force_kernel_ncu.txt")
+    try:
+        tot = 0.0
+        for l in open(path):
+            if l.startswith("dram__bytes_read.sum") or l.startswith("dram__bytes_write.sum"):
+                v, unit = l.split()[1], l.split()[2]
+                tot += float(v) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
+        if tot > 0:
+            return tot, ("from the committed ncu --set full capture profiles/r02_force_kernel_ncu.txt (N=1M single-GPU launch "
+                         "shape; algorithmic minimum ~ 50 MB j-set + boxes read once + per-split partials), not from this run")
+    except Exception:
+        pass
+    return None, "not measured in the run (DRAM bytes need ncu)"
+
+
 def _sample_errors(acc, jerk, pot, nn, ref, ids):
     """Per-particle relative errors of a sampled i-set against the oracle (north-star metric)."""
     ea = np.linalg.norm(acc - ref["acc"], axis=1) / np.linalg.norm(ref["acc"], axis=1)
@@ -484,6 +503,7 @@ def run_b200(a):
             parity["ok"] = bool(ok)
         peak_src = "nominal 148 SM x 128 lanes x 2 x 1.965 GHz (MEASURED_PEAKS.json holds no FP32 figure); " \
                    "measured FFMA microbenchmark alongside"
+        traffic, traffic_note = _committed_traffic()
         line = {
             "metric": "interactions/s", "value": value, "unit": "interactions/s", "n_gpus": world,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -502,8 +522,8 @@ def run_b200(a):
             "tflops_60": value * FLOP_PER_INTERACTION / 1e12,
             "frac_fp32_peak_nominal": value * FLOP_PER_INTERACTION / 1e12 / (NOMINAL_FP32_TFLOPS * world),
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": NOMINAL_FP32_TFLOPS, "unit": "TFLOP/s",
-                         "frac": achieved / NOMINAL_FP32_TFLOPS, "traffic": None,
-                         "traffic_note": "not measured in the run (DRAM bytes need ncu); profiles/ holds the ncu capture",
+                         "frac": achieved / NOMINAL_FP32_TFLOPS, "traffic": traffic, "traffic_unit": "bytes per launch",
+                         "traffic_note": traffic_note,
                          "peak_source": peak_src,
                          "kernel": "force_fast_kernel", "flop_per_launch": flop_per_launch,
                          "ms_per_launch": float(kms.mean()), "launches_timed": int(len(kms) * n_launch),
