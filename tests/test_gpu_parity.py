@@ -240,12 +240,14 @@ def test_block_step_sequence_across_latency_path_thresholds(g6):
                            address=sel.astype(np.int32))
 
 
-def test_bhtree_interaction_list_call_pattern(g6):
+@pytest.mark.parametrize("batched", [False, True], ids=["per-particle", "batched-replace"])
+def test_bhtree_interaction_list_call_pattern(g6, batched):
     """The third g6 caller, src/amuse_bhtree/src/BHtree.C:763-885: every tree walk
     re-sends its whole interaction list (address = index = position in the list, velocities zero,
     t = 0), then asks for the forces on the leaf's particles -- which are members of the list, so the
     self pair is excluded by id -- with nj = list length (shrinking and growing from call to call),
-    h2 = 0 and plain lasthalf."""
+    h2 = 0 and plain lasthalf.  batched: the list replaced by ONE g6x_set_j_particles call (address0 = 0) instead of
+    `length` g6_set_j_particle_ calls -- the stub INTEGRATION.md shows for BHtree.C:800-812."""
     O = _O()
     rnd = np.random.RandomState(21)
     g6.nj = 0
@@ -256,8 +258,11 @@ def test_bhtree_interaction_list_call_pattern(g6):
         mass = rnd.uniform(0.5, 1.5, length) / length
         first_leaf = int(rnd.randint(0, length - ni + 1))
         g6.set_ti(0.0)
-        for i in range(length):
-            g6.set_j_particle(i, i, 0.0, 0.0, mass[i], z, z, z, z, pos[i])
+        if batched:
+            g6.set_j_particles(np.arange(length, dtype=np.int32), mass, pos, np.zeros_like(pos))
+        else:
+            for i in range(length):
+                g6.set_j_particle(i, i, 0.0, 0.0, mass[i], z, z, z, z, pos[i])
         idx = np.arange(first_leaf, first_leaf + ni, dtype=np.int32)
         vel0 = np.zeros((ni, 3))
         out = g6.calc(idx, pos[idx], vel0, 1e-4, nj=length, want_nn=False)
