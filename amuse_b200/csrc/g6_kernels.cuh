@@ -37,6 +37,9 @@ constexpr int TILE = 256;      // j-particles per shared-memory stage
 constexpr int STAGES = 3;      // TMA bulk-copy pipeline depth
 constexpr int GROUPS_PER_TILE = TILE / 32;
 constexpr int TBOX = 2 * GROUPS_PER_TILE + 2;   // float4 per tile in gbb: 8 group boxes + the tile's own box
+#ifndef G6_DENSE_ROUNDS
+#define G6_DENSE_ROUNDS 4   // masked kernels, dense FP64 pass: particles per warp whose lanes are summed with shuffles first
+#endif
 constexpr int CTA_WL = 768;    // FP64 pairs a CTA of a masked kernel can queue (more are evaluated in place)
 #ifndef G6_FLUSH
 #define G6_FLUSH 16
@@ -1218,7 +1221,7 @@ __global__ void __launch_bounds__(THREADS, MINB) force_kernel(const __grid_const
             // let one lane add the seven totals (hundreds of pairs per particle would otherwise queue up on seven
             // addresses); with many particles per warp the lanes add their own
             unsigned int todo = __ballot_sync(0xffffffffu, wi >= 0);
-            for (int round = 0; round < 4 && todo; round++) {
+            for (int round = 0; round < G6_DENSE_ROUNDS && todo; round++) {
                 const int cur = __shfl_sync(0xffffffffu, wi, __ffs(todo) - 1);
                 const bool mine = (wi == cur);
                 const unsigned int grp = __ballot_sync(0xffffffffu, mine);
